@@ -1,0 +1,259 @@
+"""GpuCodec: the batched blob codec behind ContentAddressedStore (pack = SHA-1 + gzip, unpack = gunzip).
+
+It replaces, for a whole batch at a time, the three per-blob calls of the reference
+(metaflow/datastore/content_addressed_store.py:98 sha1, :114/:211-216 _pack_v1, :192/:218-220
+_unpack_v1) with mfcas_pack_batch / mfcas_hash_batch / mfcas_unpack_batch on the GPUs.
+Blobs are packed into page-locked arenas so every wave moves with one cudaMemcpyAsync each way.
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from .exception import DataException, GpuCasUnavailable
+from . import metaflow_config
+
+_ALIGN = 256
+
+
+def _align(n):
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+class _PinnedArena(object):
+    """A grow-only page-locked byte buffer exposed as a numpy uint8 array."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self._ptr = None
+        self.cap = 0
+        self.arr = None
+
+    def ensure(self, nbytes):
+        if nbytes <= self.cap:
+            return
+        self.release()
+        want = int(nbytes + nbytes // 8 + 4096)
+        p = self._lib.mfcas_alloc_pinned(want)
+        if not p:
+            raise MemoryError("mfcas_alloc_pinned(%d) failed" % want)
+        self._ptr = p
+        self.cap = want
+        self.arr = np.ctypeslib.as_array((ctypes.c_uint8 * want).from_address(p))
+
+    @property
+    def base(self):
+        return self._ptr
+
+    def release(self):
+        if self._ptr:
+            self.arr = None
+            self._lib.mfcas_free_pinned(self._ptr)
+            self._ptr = None
+            self.cap = 0
+
+
+def _as_u8(blob):
+    if isinstance(blob, np.ndarray) and blob.dtype == np.uint8 and blob.ndim == 1:
+        return blob
+    return np.frombuffer(blob, dtype=np.uint8)
+
+
+class UnpackError(Exception):
+    """Per-blob decode failure; str() mirrors the message the reference's gzip reader gives."""
+
+    def __init__(self, code):
+        self.code = code
+        super().__init__(capi.STATUS_TEXT.get(code, "error %d" % code))
+
+
+class GpuCodec(object):
+    def __init__(self, devices=None, wave_bytes=None, lz=None):
+        lib = capi.load()
+        if lib.mfcas_device_count() <= 0:
+            raise GpuCasUnavailable("no CUDA device visible: the artifact hot path has no CPU fallback")
+        if devices is None and metaflow_config.GPU_CAS_DEVICES:
+            devices = [int(x) for x in str(metaflow_config.GPU_CAS_DEVICES).split(",") if x != ""]
+        if wave_bytes is None:
+            wave_bytes = int(metaflow_config.GPU_CAS_WAVE_BYTES)
+        if lz is None:
+            lz = bool(int(metaflow_config.GPU_CAS_LZ))
+        flags = 0 if lz else capi.FLAG_NO_LZ
+        if devices:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            ctx = lib.mfcas_create(arr, len(devices), wave_bytes, flags)
+        else:
+            ctx = lib.mfcas_create(None, 0, wave_bytes, flags)
+        if not ctx:
+            raise GpuCasUnavailable("mfcas_create failed (no usable CUDA device or out of memory)")
+        self._lib = lib
+        self._ctx = ctypes.c_void_p(ctx)
+        self._in = _PinnedArena(lib)
+        self._out = _PinnedArena(lib)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._in.release()
+            self._out.release()
+            self._lib.mfcas_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != capi.OK:
+            raise DataException("GPU codec call failed (%s): %s" % (
+                capi.STATUS_TEXT.get(rc, rc), self._lib.mfcas_last_error(self._ctx).decode("utf-8", "replace")))
+
+    def _stage_inputs(self, blobs):
+        n = len(blobs)
+        lens = np.fromiter((len(b) for b in blobs), dtype=np.uint64, count=n)
+        offs = np.zeros(n, dtype=np.uint64)
+        total = 0
+        for i in range(n):
+            offs[i] = total
+            total += _align(int(lens[i])) + _ALIGN
+        self._in.ensure(total + _ALIGN)
+        arr = self._in.arr
+        for i, b in enumerate(blobs):
+            ln = int(lens[i])
+            if ln:
+                o = int(offs[i])
+                arr[o:o + ln] = _as_u8(b)
+        src = (offs + np.uint64(self._in.base)).astype(np.uint64)
+        return lens, src
+
+    @staticmethod
+    def _pp(a):
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_void_p))
+
+    @staticmethod
+    def _p64(a):
+        return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+    # ------------------------------------------------------------------ save side
+    def hash_batch(self, blobs):
+        """-> list of 40-hex SHA-1 keys (content_addressed_store.py:98)."""
+        n = len(blobs)
+        if n == 0:
+            return []
+        lens, src = self._stage_inputs(blobs)
+        sha = np.empty(20 * n, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.mfcas_hash_batch(self._ctx, n, self._pp(src), self._p64(lens), sha.ctypes.data,
+                                               st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        raw = sha.tobytes()
+        return [raw[20 * i:20 * i + 20].hex() for i in range(n)]
+
+    def pack_batch(self, blobs):
+        """-> (keys, packed) where packed[i] is a memoryview over page-locked memory holding the
+        RFC 1952 bytes of blob i.  The views stay valid until the next pack/unpack call."""
+        n = len(blobs)
+        if n == 0:
+            return [], []
+        lens, src = self._stage_inputs(blobs)
+        caps = np.fromiter((self._lib.mfcas_pack_bound(int(x)) for x in lens), dtype=np.uint64, count=n)
+        ooffs = np.zeros(n, dtype=np.uint64)
+        total = 0
+        for i in range(n):
+            ooffs[i] = total
+            total += _align(int(caps[i])) + _ALIGN
+        self._out.ensure(total + _ALIGN)
+        dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
+        dlen = np.zeros(n, dtype=np.uint64)
+        sha = np.empty(20 * n, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.mfcas_pack_batch(self._ctx, n, self._pp(src), self._p64(lens), self._pp(dst), self._p64(caps),
+                                               self._p64(dlen), sha.ctypes.data, st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        if st.any():
+            bad = int(np.flatnonzero(st)[0])
+            raise DataException("GPU pack failed for blob %d: %s" % (bad, capi.STATUS_TEXT.get(int(st[bad]), st[bad])))
+        raw = sha.tobytes()
+        keys = [raw[20 * i:20 * i + 20].hex() for i in range(n)]
+        mv = memoryview(self._out.arr)
+        packed = [mv[int(ooffs[i]):int(ooffs[i]) + int(dlen[i])] for i in range(n)]
+        return keys, packed
+
+    # ------------------------------------------------------------------ load side
+    def unpacked_size(self, packed):
+        a = _as_u8(packed)
+        size = ctypes.c_uint64(0)
+        exact = ctypes.c_int(0)
+        rc = self._lib.mfcas_unpacked_size(a.ctypes.data, a.size, ctypes.byref(size), ctypes.byref(exact))
+        if rc != capi.OK:
+            raise UnpackError(rc)
+        return size.value, bool(exact.value)
+
+    def unpack_batch(self, packed_blobs, as_bytes=True):
+        """-> list with, per blob, the decoded bytes (or a memoryview over pinned memory when
+        as_bytes=False, valid until the next call) or an UnpackError instance."""
+        n = len(packed_blobs)
+        if n == 0:
+            return []
+        results = [None] * n
+        sizes = np.zeros(n, dtype=np.uint64)
+        todo = []
+        for i, p in enumerate(packed_blobs):
+            try:
+                sizes[i], _ = self.unpacked_size(p)
+                todo.append(i)
+            except UnpackError as e:
+                results[i] = e
+        attempt = 0
+        while todo:
+            blobs = [packed_blobs[i] for i in todo]
+            lens, src = self._stage_inputs(blobs)
+            m = len(todo)
+            caps = np.array([int(sizes[i]) for i in todo], dtype=np.uint64)
+            ooffs = np.zeros(m, dtype=np.uint64)
+            total = 0
+            for k in range(m):
+                ooffs[k] = total
+                total += _align(int(caps[k])) + _ALIGN
+            self._out.ensure(total + _ALIGN)
+            dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
+            dlen = np.zeros(m, dtype=np.uint64)
+            st = np.zeros(m, dtype=np.int32)
+            self._check(self._lib.mfcas_unpack_batch(self._ctx, m, self._pp(src), self._p64(lens), self._pp(dst), self._p64(caps),
+                                                     self._p64(dlen), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+            mv = memoryview(self._out.arr)
+            retry = []
+            for k, i in enumerate(todo):
+                code = int(st[k])
+                if code == capi.OK:
+                    view = mv[int(ooffs[k]):int(ooffs[k]) + int(dlen[k])]
+                    results[i] = bytes(view) if (as_bytes or retry) else view
+                elif code == capi.E_DST_TOO_SMALL and attempt < 8:
+                    # foreign multi-member / >4 GiB streams: the ISIZE hint was short -- grow and retry
+                    sizes[i] = max(int(dlen[k]), 2 * int(sizes[i]) + 65536)
+                    retry.append(i)
+                else:
+                    results[i] = UnpackError(code)
+            if retry and not as_bytes:
+                # views of this round die when the arena is reused: materialise them
+                for i in todo:
+                    if isinstance(results[i], memoryview):
+                        results[i] = bytes(results[i])
+            todo = retry
+            attempt += 1
+        return results
+
+    def counters(self):
+        a, b, c = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        self._lib.mfcas_counters(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"kernel_launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
+
+
+_default = None
+
+
+def default_codec():
+    """Process-wide GpuCodec; raises GpuCasUnavailable when the GPU path cannot run."""
+    global _default
+    if _default is None:
+        _default = GpuCodec()
+    return _default

@@ -1,0 +1,495 @@
+// mf_deflate.cuh -- chunk-parallel DEFLATE encoder + CRC-32 for sm_100a, and the gather pass
+// that assembles RFC 1952 members.
+//
+// Replaces ContentAddressedStore._pack_v1 (metaflow/datastore/content_addressed_store.py:211-216:
+// gzip.GzipFile(compresslevel=3).write -> zlib deflate + zlib.crc32, /usr/lib/python3.12/gzip.py
+// :259-285, :302-314, :350-360).  Output is a different (chunked, indexed) but equally valid
+// RFC 1952 byte stream: parity is defined on the decoded bytes.
+//
+// One CTA (16 warps) owns one 32 KiB chunk staged in shared memory:
+//   pass 0  coalesced 16-byte loads HBM -> smem
+//   pass 1  CRC-32 of the chunk (64-byte piece per lane, slice-by-4 tables in smem, GF(2) combine)
+//   pass 2  LZ77: each warp walks its 1 KiB segments 32 positions at a time (hash probe + in-window
+//           probes via warp shuffles, cooperative match extension, ballot-ordered greedy parse)
+//   pass 3  CTA-parallel Huffman construction (bitonic sort, two-queue merge, Kraft repair)
+//   pass 4  per-lane bit counting, warp-shuffle prefix scans -> every token's bit offset
+//   pass 5  bit packing into smem, then coalesced 16-byte stores smem -> HBM slot
+// HBM traffic per chunk: raw bytes read once, packed bytes written once (+ the gather copy).
+#pragma once
+#include <cuda_runtime.h>
+#include "mf_core.h"
+
+struct MfEncMember {
+    const uint8_t *src;     // device pointer to the member's raw bytes (16-byte aligned)
+    uint32_t raw_len;       // <= MF_MEMBER_RAW
+    uint32_t n_chunks;
+    uint32_t first_chunk;   // global chunk index of chunk 0
+    uint32_t blob;          // owning blob
+};
+
+struct MfEncBlob {
+    uint8_t *dst;           // device pointer where the packed blob goes
+    uint64_t dst_cap;
+    uint32_t first_member;
+    uint32_t n_members;
+};
+
+__device__ __forceinline__ uint32_t mf_ld32u(const uint8_t *base, uint32_t off) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+    uint32_t i = off >> 2;
+    return __funnelshift_r(w[i], w[i + 1], (off & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t mf_warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t u = __shfl_up_sync(0xFFFFFFFFu, v, d);
+        if ((int)lane >= d) v += u;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t mf_warp_xor(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v ^= __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+
+// slice-by-4 tables for the reflected CRC-32: T[k][b] = raw crc of byte b followed by k zero bytes
+__device__ uint32_t g_mf_crc_tab[4][256];
+// x^(8*64*j) mod P for j = 0..511: multiplier that moves a 64-byte piece's raw CRC j pieces left
+__device__ uint32_t g_mf_piece_mul[512];
+
+__global__ void mf_init_tables_kernel() {
+    int t = threadIdx.x + blockIdx.x * blockDim.x;
+    if (t < 256) {
+        uint32_t c = (uint32_t)t;
+        for (int k = 0; k < 8; k++) c = (c >> 1) ^ ((c & 1u) ? MF_CRC_POLY : 0u);
+        g_mf_crc_tab[0][t] = c;
+        uint32_t c1 = c;
+        for (int s = 1; s < 4; s++) {
+            // append one zero byte: crc' = T0[crc & 0xFF] ^ (crc >> 8); T0 entry recomputed bitwise
+            uint32_t lo = c1 & 0xFFu, x = lo;
+            for (int k = 0; k < 8; k++) x = (x >> 1) ^ ((x & 1u) ? MF_CRC_POLY : 0u);
+            c1 = x ^ (c1 >> 8);
+            g_mf_crc_tab[s][t] = c1;
+        }
+    }
+    if (t < 512) g_mf_piece_mul[t] = mf_xpow8(64ull * (uint64_t)t);
+}
+
+// raw (zero-init, no final xor) CRC of `n` bytes (n multiple of 4) at smem offset `off` (multiple of 4)
+__device__ __forceinline__ uint32_t mf_crc_words(const uint8_t *s, uint32_t off, uint32_t n, const uint32_t (*T)[256]) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s + off);
+    uint32_t crc = 0;
+    for (uint32_t i = 0; i < (n >> 2); i++) {
+        uint32_t x = crc ^ w[i];
+        crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24];
+    }
+    return crc;
+}
+
+#define MF_ENC_THREADS 512
+#define MF_ENC_WARPS 16
+#define MF_HASH_BITS 10
+#define MF_REGION_B 34816u      // hash tables in pass 2 (32 KiB), packed output words afterwards
+
+struct __align__(16) MfEncSmem {
+    uint8_t data[MF_CHUNK + 32];
+    uint8_t regionB[MF_REGION_B];
+    uint32_t match[MF_SEGS_PER_CHUNK][MF_MAXM];
+    uint32_t crc_tab[4][256];
+    uint32_t ll_hist[288];
+    uint32_t d_hist[32];
+    uint32_t ll_codes[288];
+    uint32_t d_codes[32];
+    uint8_t ll_lens[288];
+    uint8_t d_lens[32];
+    MfHuffScratch huff;
+    MfHdrScratch hdr;
+    uint32_t nmatch[MF_SEGS_PER_CHUNK];
+    uint32_t seg_bits[MF_SEGS_PER_CHUNK];
+    uint32_t seg_off[MF_SEGS_PER_CHUNK];
+    uint16_t lane_bits[MF_SEGS_PER_CHUNK][32];
+    uint32_t crc_part[MF_ENC_WARPS];
+    uint32_t total_bits;
+    uint32_t comp_bytes;
+    uint32_t stored;
+};
+
+// flags bit 0: MFCAS_FLAG_NO_LZ
+__global__ void __launch_bounds__(MF_ENC_THREADS, 2)
+mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__restrict__ chunk_member, uint32_t n_chunks_total,
+                  uint8_t *__restrict__ slots, uint32_t *__restrict__ comp_bytes_out, uint16_t *__restrict__ hdr_bits_out,
+                  uint16_t *__restrict__ seg_bits_out, uint32_t *__restrict__ chunk_crc_out, uint32_t flags) {
+    extern __shared__ __align__(16) uint8_t mf_smem_raw[];
+    MfEncSmem &S = *reinterpret_cast<MfEncSmem *>(mf_smem_raw);
+    const uint32_t c = blockIdx.x;
+    if (c >= n_chunks_total) return;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const MfEncMember mem = members[chunk_member[c]];
+    const uint32_t ci = c - mem.first_chunk;
+    const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
+    const uint8_t *src = mem.src + (size_t)ci * MF_CHUNK;
+
+    // ---- pass 0: stage the chunk, zero histograms, copy CRC tables
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(src);
+        uint4 *s = reinterpret_cast<uint4 *>(S.data);
+        uint32_t nv = (len + 15u) >> 4;
+        for (uint32_t i = tid; i < nv; i += MF_ENC_THREADS) s[i] = __ldg(g + i);
+        for (uint32_t i = nv + tid; i < (MF_CHUNK + 32) / 16; i += MF_ENC_THREADS) s[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid; i < 1024; i += MF_ENC_THREADS) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
+        for (uint32_t i = tid; i < 288; i += MF_ENC_THREADS) S.ll_hist[i] = 0;
+        if (tid < 32) S.d_hist[tid] = 0;
+    }
+    __syncthreads();
+    // bytes past `len` inside the last 16-byte vector came from the (padded) source: clear them so
+    // that nothing downstream depends on them
+    if (tid < 16 && (len & 15u) && tid >= (len & 15u)) S.data[(len & ~15u) + tid] = 0;
+    __syncthreads();
+
+    // ---- pass 1: CRC-32 (raw, zero init) of the chunk; piece g = 64 bytes [64g, 64g+64)
+    {
+        uint32_t g = tid;                       // 512 pieces
+        uint32_t start = g * 64u;
+        uint32_t crc = 0;
+        if (start < len) {
+            uint32_t end = min(start + 64u, len);
+            uint32_t nw = (end - start) & ~3u;
+            crc = mf_crc_words(S.data, start, nw, S.crc_tab);
+            for (uint32_t p = start + nw; p < end; p++) crc = S.crc_tab[0][(crc ^ S.data[p]) & 0xFFu] ^ (crc >> 8);
+            uint32_t after = len - end;          // bytes of the chunk after this piece
+            uint32_t mul = (len == MF_CHUNK) ? g_mf_piece_mul[511u - g] : mf_xpow8(after);
+            crc = mf_gf2_mul(crc, mul);
+        }
+        crc = mf_warp_xor(crc);
+        if (lane == 0) S.crc_part[warp] = crc;
+    }
+
+    // ---- pass 2: LZ77 over this warp's two segments
+    {
+        uint16_t *ht = reinterpret_cast<uint16_t *>(S.regionB) + warp * (1u << MF_HASH_BITS);
+        const bool lz = (flags & 1u) == 0;
+        for (uint32_t si = 0; si < 2; si++) {
+            const uint32_t seg = warp * 2 + si;
+            const uint32_t base = seg * MF_SEG;
+            if (base >= len) { if (lane == 0) S.nmatch[seg] = 0; continue; }
+            const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
+            for (uint32_t i = lane; i < (1u << MF_HASH_BITS) / 2; i += 32) reinterpret_cast<uint32_t *>(ht)[i] = 0;
+            __syncwarp();
+            uint32_t nm = 0;
+            uint32_t *ml = S.match[seg];
+            uint32_t pos = 0;
+            while (pos < seglen) {
+                const uint32_t p = pos + lane;
+                const bool valid = p < seglen;
+                const uint32_t w = valid ? mf_ld32u(S.data, base + p) : 0u;
+                const bool can = lz && (p + MF_MIN_MATCH <= seglen) && (nm < MF_MAXM);
+                const uint32_t h = (w * 2654435761u) >> (32 - MF_HASH_BITS);
+                int q = -1;
+                if (can) { uint32_t cnd = ht[h]; if (cnd) q = (int)cnd - 1; }
+                __syncwarp();
+                if (can) ht[h] = (uint16_t)(p + 1);
+                __syncwarp();
+                // in-window probes (the hash table only knows earlier windows)
+                {
+                    uint32_t w8 = __shfl_up_sync(0xFFFFFFFFu, w, 8);
+                    uint32_t w4 = __shfl_up_sync(0xFFFFFFFFu, w, 4);
+                    uint32_t w2 = __shfl_up_sync(0xFFFFFFFFu, w, 2);
+                    uint32_t w1 = __shfl_up_sync(0xFFFFFFFFu, w, 1);
+                    if (can) {
+                        if (lane >= 8 && w8 == w) q = (int)p - 8;
+                        if (lane >= 4 && w4 == w) q = (int)p - 4;
+                        if (lane >= 2 && w2 == w) q = (int)p - 2;
+                        if (lane >= 1 && w1 == w) q = (int)p - 1;
+                    }
+                }
+                bool has = false;
+                if (can && q >= 0) has = (mf_ld32u(S.data, base + (uint32_t)q) == w);
+                uint32_t bal = __ballot_sync(0xFFFFFFFFu, has);
+                const uint32_t validmask = __ballot_sync(0xFFFFFFFFu, valid);
+                uint32_t litmask = 0;
+                uint32_t cur = 0, adv = 32;
+                while (true) {
+                    uint32_t m = cur < 32 ? (bal & (0xFFFFFFFFu << cur)) : 0u;
+                    if (!m) { if (cur < 32) litmask |= (0xFFFFFFFFu << cur); adv = 32; break; }
+                    const uint32_t L = __ffs(m) - 1;
+                    const uint32_t pL = pos + L;
+                    const uint32_t qL = (uint32_t)__shfl_sync(0xFFFFFFFFu, q, L);
+                    const uint32_t maxlen = min((uint32_t)MF_MAX_MATCH, seglen - pL);
+                    uint32_t mlen = maxlen;
+                    for (uint32_t off = 4; off < maxlen; off += 32) {
+                        uint32_t o = off + lane;
+                        bool ne = (o >= maxlen) || (S.data[base + pL + o] != S.data[base + qL + o]);
+                        uint32_t bm = __ballot_sync(0xFFFFFFFFu, ne);
+                        if (bm) { mlen = off + (__ffs(bm) - 1); break; }
+                    }
+                    const uint32_t dist = pL - qL;
+                    const bool accept = (mlen >= 6) || (mlen >= 4 && dist <= 32) || (mlen == 5 && dist <= 256);
+                    if (accept) {
+                        if (L > cur) litmask |= ((1u << L) - 1u) & (0xFFFFFFFFu << cur);
+                        if (lane == 0) {
+                            ml[nm] = mf_match_pack(pL, mlen, dist);
+                            uint32_t ls, lb, lv, ds, db, dv;
+                            mf_len_sym(mlen, ls, lb, lv); mf_dist_sym(dist, ds, db, dv);
+                            atomicAdd(&S.ll_hist[ls], 1u);
+                            atomicAdd(&S.d_hist[ds], 1u);
+                        }
+                        nm++;
+                        if (nm >= MF_MAXM) bal = 0;
+                        const uint32_t e = L + mlen;
+                        if (e >= 32) { adv = e; break; }
+                        cur = e;
+                    } else {
+                        litmask |= ((L == 31 ? 0xFFFFFFFFu : ((1u << (L + 1)) - 1u))) & (0xFFFFFFFFu << cur);
+                        cur = L + 1;
+                    }
+                }
+                litmask &= validmask;
+                if ((litmask >> lane) & 1u) atomicAdd(&S.ll_hist[w & 0xFFu], 1u);
+                pos += adv;
+            }
+            if (lane == 0) S.nmatch[seg] = nm;
+        }
+    }
+    if (tid == 0) S.ll_hist[256] = 1;       // end-of-block
+    __syncthreads();
+
+    // ---- pass 3: Huffman codes, block header
+    mf_huff_build<512>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.huff);
+    mf_huff_build<32>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.huff);
+    if (tid == 0) mf_hdr_rle(S.ll_lens, S.d_lens, S.hdr);
+    {   // region B is dead as hash tables now: zero it for the bit writers
+        uint4 *z = reinterpret_cast<uint4 *>(S.regionB);
+        for (uint32_t i = tid; i < MF_REGION_B / 16; i += MF_ENC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    mf_huff_build<32>(S.hdr.clhist, 19, 7, S.hdr.cllens, S.hdr.clcodes, S.huff);
+    uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
+    if (tid == 0) mf_hdr_write(outw, S.hdr);
+    __syncthreads();
+
+    // ---- pass 4: bit counts per lane, per segment
+    for (uint32_t si = 0; si < 2; si++) {
+        const uint32_t seg = warp * 2 + si;
+        const uint32_t base = seg * MF_SEG;
+        uint32_t bits = 0;
+        if (base < len) {
+            const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
+            bits = mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, nullptr);
+        }
+        S.lane_bits[seg][lane] = (uint16_t)bits;
+        uint32_t incl = mf_warp_incl_scan(bits, lane);
+        if (lane == 31) S.seg_bits[seg] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t b = S.seg_bits[lane];
+        uint32_t incl = mf_warp_incl_scan(b, lane);
+        S.seg_off[lane] = S.hdr.hdr_bits + incl - b;
+        if (lane == 31) {
+            uint32_t eob = S.ll_codes[256];
+            uint32_t end_tokens = S.hdr.hdr_bits + incl;            // where EOB goes
+            uint32_t end_bits = end_tokens + (eob >> 16) + 3u;       // + empty stored block header (000)
+            uint32_t dyn_bytes = ((end_bits + 7u) >> 3) + 4u;        // + LEN/NLEN of the sync marker
+            S.total_bits = end_tokens;
+            if (dyn_bytes >= len + 5u) { S.stored = 1; S.comp_bytes = len + 5u; }
+            else { S.stored = 0; S.comp_bytes = dyn_bytes; }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 5: pack
+    if (!S.stored) {
+        for (uint32_t si = 0; si < 2; si++) {
+            const uint32_t seg = warp * 2 + si;
+            const uint32_t base = seg * MF_SEG;
+            if (base >= len) continue;
+            const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
+            uint32_t bits = S.lane_bits[seg][lane];
+            uint32_t incl = mf_warp_incl_scan(bits, lane);
+            if (bits) {
+                MfBitWriter bw;
+                bw.init(outw, S.seg_off[seg] + incl - bits);
+                mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, &bw);
+                bw.flush();
+            }
+        }
+        if (tid == 0) {
+            MfBitWriter bw;
+            bw.init(outw, S.total_bits);
+            uint32_t eob = S.ll_codes[256];
+            bw.put(eob & 0xFFFFu, eob >> 16);
+            bw.flush();
+            // sync marker: 3 zero bits, pad to byte, 00 00 FF FF (words are zero already)
+            uint32_t end_bits = S.total_bits + (eob >> 16) + 3u;
+            uint32_t byte = ((end_bits + 7u) >> 3) + 2u;
+            uint8_t *ob = S.regionB;
+            atomicOr(&outw[byte >> 2], 0xFFu << ((byte & 3u) * 8u));
+            atomicOr(&outw[(byte + 1) >> 2], 0xFFu << (((byte + 1) & 3u) * 8u));
+            (void)ob;
+        }
+    } else {
+        // stored block: 00 | LEN | NLEN | raw bytes (byte-aligned by construction)
+        uint32_t nwords = (len + 5u + 3u) >> 2;
+        for (uint32_t j = tid; j < nwords; j += MF_ENC_THREADS) {
+            uint32_t v;
+            if (j == 0) v = 0x00u | ((len & 0xFFFFu) << 8) | (((~len) & 0xFFu) << 24);
+            else if (j == 1) v = (((~len) >> 8) & 0xFFu) | ((uint32_t)S.data[0] << 8) | ((uint32_t)S.data[1] << 16) | ((uint32_t)S.data[2] << 24);
+            else v = mf_ld32u(S.data, 4u * j - 5u);
+            outw[j] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- write out: slot bytes, index entries, chunk CRC
+    {
+        const uint32_t cb = S.comp_bytes;
+        uint4 *g = reinterpret_cast<uint4 *>(slots + (size_t)c * MF_SLOT);
+        const uint4 *s = reinterpret_cast<const uint4 *>(S.regionB);
+        for (uint32_t i = tid; i < ((cb + 15u) >> 4); i += MF_ENC_THREADS) g[i] = s[i];
+        if (tid < MF_SEGS_PER_CHUNK) seg_bits_out[(size_t)c * MF_SEGS_PER_CHUNK + tid] = S.stored ? 0 : (uint16_t)S.seg_bits[tid];
+        if (tid == 0) {
+            comp_bytes_out[c] = cb;
+            hdr_bits_out[c] = S.stored ? (uint16_t)MF_STORED_MARK : (uint16_t)S.hdr.hdr_bits;
+            uint32_t crc = 0;
+            for (int k = 0; k < MF_ENC_WARPS; k++) crc ^= S.crc_part[k];
+            chunk_crc_out[c] = crc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ gather: members -> final bytes
+__device__ __forceinline__ void mf_put_le16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+__device__ __forceinline__ void mf_put_le32(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+
+#define MF_GA_THREADS 256
+// One CTA per blob: lays out its members, writes gzip headers + index + trailers, records where
+// every chunk's bytes go.  chunk_dst[c] = byte offset inside the blob's dst, or ~0 when the blob
+// does not fit dst_cap (status DST_TOO_SMALL).
+__global__ void __launch_bounds__(MF_GA_THREADS)
+mf_gather_layout_kernel(const MfEncBlob *__restrict__ blobs, const MfEncMember *__restrict__ members,
+                        const uint32_t *__restrict__ comp_bytes, const uint16_t *__restrict__ hdr_bits,
+                        const uint16_t *__restrict__ seg_bits, const uint32_t *__restrict__ chunk_crc,
+                        uint64_t *__restrict__ chunk_dst, uint64_t *__restrict__ dst_len, int32_t *__restrict__ status) {
+    __shared__ uint32_t s_scan[MF_GA_THREADS];
+    __shared__ uint32_t s_crc[MF_GA_THREADS];
+    __shared__ uint64_t s_off;
+    __shared__ int s_fit;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x;
+    const MfEncBlob blob = blobs[b];
+    // first walk: total size (so that an undersized dst is never written)
+    if (tid == 0) { s_off = 0; }
+    __syncthreads();
+    uint64_t total = 0;
+    for (uint32_t mi = 0; mi < blob.n_members; mi++) {
+        const MfEncMember mem = members[blob.first_member + mi];
+        uint32_t part = 0;
+        for (uint32_t k = tid; k < mem.n_chunks; k += MF_GA_THREADS) part += comp_bytes[mem.first_chunk + k];
+        s_scan[tid] = part;
+        __syncthreads();
+        for (int d = MF_GA_THREADS / 2; d > 0; d >>= 1) { if ((int)tid < d) s_scan[tid] += s_scan[tid + d]; __syncthreads(); }
+        total += (uint64_t)mf_member_header_bytes(mem.n_chunks) + s_scan[0] + MF_TRAILER;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        s_fit = total <= blob.dst_cap;
+        dst_len[b] = total;
+        status[b] = s_fit ? 0 : 1 /* MFCAS_E_DST_TOO_SMALL */;
+    }
+    __syncthreads();
+    const bool fit = s_fit != 0;
+    uint64_t off = 0;
+    for (uint32_t mi = 0; mi < blob.n_members; mi++) {
+        const MfEncMember mem = members[blob.first_member + mi];
+        const uint32_t nc = mem.n_chunks;
+        const uint32_t hdr = mf_member_header_bytes(nc);
+        // exclusive scan of comp_bytes over this member's chunks (<= 768 = 3 per thread, blocked)
+        const uint32_t per = (nc + MF_GA_THREADS - 1) / MF_GA_THREADS;
+        uint32_t mine = 0;
+        for (uint32_t k = 0; k < per; k++) { uint32_t ch = tid * per + k; if (ch < nc) mine += comp_bytes[mem.first_chunk + ch]; }
+        s_scan[tid] = mine;
+        __syncthreads();
+        for (int d = 1; d < MF_GA_THREADS; d <<= 1) {
+            uint32_t v = (int)tid >= d ? s_scan[tid - d] : 0u;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const uint32_t payload = s_scan[MF_GA_THREADS - 1];
+        uint32_t run = s_scan[tid] - mine;                 // exclusive prefix of this thread's first chunk
+        uint32_t crc_acc = 0;
+        uint8_t *mbase = blob.dst + off;
+        for (uint32_t k = 0; k < per; k++) {
+            uint32_t ch = tid * per + k;
+            if (ch >= nc) break;
+            const uint32_t gc = mem.first_chunk + ch;
+            const uint32_t cb = comp_bytes[gc];
+            chunk_dst[gc] = fit ? (off + hdr + run) : ~0ull;
+            // CRC contribution: chunk raw CRC shifted left by the raw bytes that follow it
+            uint64_t chunk_end = min((uint64_t)(ch + 1) * MF_CHUNK, (uint64_t)mem.raw_len);
+            crc_acc ^= mf_gf2_mul(chunk_crc[gc], mf_xpow8((uint64_t)mem.raw_len - chunk_end));
+            if (fit) {
+                uint8_t *e = mbase + MF_HDR_FIXED + (size_t)ch * 8u;
+                mf_put_le32(e, cb); mf_put_le16(e + 4, hdr_bits[gc]); mf_put_le16(e + 6, 0);
+                uint8_t *sb = mbase + MF_HDR_FIXED + (size_t)nc * 8u + (size_t)ch * 64u;
+                for (uint32_t s = 0; s < MF_SEGS_PER_CHUNK; s++) mf_put_le16(sb + 2 * s, seg_bits[(size_t)gc * MF_SEGS_PER_CHUNK + s]);
+            }
+            run += cb;
+        }
+        s_crc[tid] = crc_acc;
+        __syncthreads();
+        for (int d = MF_GA_THREADS / 2; d > 0; d >>= 1) { if ((int)tid < d) s_crc[tid] ^= s_crc[tid + d]; __syncthreads(); }
+        if (tid == 0 && fit) {
+            uint8_t *h = mbase;
+            h[0] = 0x1f; h[1] = 0x8b; h[2] = 8; h[3] = 4 /* FEXTRA */;
+            h[4] = h[5] = h[6] = h[7] = 0;              /* MTIME 0: deterministic output */
+            h[8] = 0; h[9] = 255;                        /* XFL 0, OS unknown (as gzip.py writes) */
+            mf_put_le16(h + 10, hdr - 12);               /* XLEN */
+            h[12] = 'M'; h[13] = 'F'; mf_put_le16(h + 14, hdr - 16);
+            h[16] = MF_FORMAT_VERSION; h[17] = MF_CHUNK_LOG2; h[18] = MF_SEG_LOG2; h[19] = 0;
+            mf_put_le32(h + 20, mem.raw_len); mf_put_le32(h + 24, nc); mf_put_le32(h + 28, 0);
+            uint8_t *t = mbase + hdr + payload;
+            t[0] = 1; t[1] = 0; t[2] = 0; t[3] = 0xFF; t[4] = 0xFF;   /* final empty stored block */
+            mf_put_le32(t + 5, mf_crc_finish(s_crc[0], mem.raw_len));
+            mf_put_le32(t + 9, mem.raw_len);
+        }
+        off += (uint64_t)hdr + payload + MF_TRAILER;
+        __syncthreads();
+    }
+}
+
+// One CTA per chunk: slot (16-byte aligned) -> final position (any alignment).
+__global__ void __launch_bounds__(256)
+mf_gather_copy_kernel(const MfEncBlob *__restrict__ blobs, const MfEncMember *__restrict__ members,
+                      const uint32_t *__restrict__ chunk_member, uint32_t n_chunks_total,
+                      const uint8_t *__restrict__ slots, const uint32_t *__restrict__ comp_bytes,
+                      const uint64_t *__restrict__ chunk_dst) {
+    const uint32_t c = blockIdx.x;
+    if (c >= n_chunks_total) return;
+    const uint64_t doff = chunk_dst[c];
+    if (doff == ~0ull) return;
+    uint8_t *dst = blobs[members[chunk_member[c]].blob].dst + doff;
+    const uint8_t *src = slots + (size_t)c * MF_SLOT;
+    const uint32_t n = comp_bytes[c];
+    const uint32_t tid = threadIdx.x;
+    // head: bytes until dst is 16-byte aligned
+    uint32_t head = (uint32_t)((16u - ((uintptr_t)dst & 15u)) & 15u);
+    if (head > n) head = n;
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t body = (n - head) >> 4;           // whole 16-byte vectors
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(src);
+    uint4 *dv = reinterpret_cast<uint4 *>(dst + head);
+    const uint32_t sh = (head & 3u) * 8u;
+    const uint32_t w0 = head >> 2;
+    for (uint32_t v = tid; v < body; v += blockDim.x) {
+        const uint32_t i = w0 + 4u * v;
+        uint32_t a = sw[i], b = sw[i + 1], cc = sw[i + 2], d = sw[i + 3], e = sh ? sw[i + 4] : 0u;
+        uint4 o;
+        o.x = __funnelshift_r(a, b, sh); o.y = __funnelshift_r(b, cc, sh);
+        o.z = __funnelshift_r(cc, d, sh); o.w = __funnelshift_r(d, e, sh);
+        dv[v] = o;
+    }
+    const uint32_t done = head + (body << 4);
+    if (tid < n - done) dst[done + tid] = src[done + tid];
+}

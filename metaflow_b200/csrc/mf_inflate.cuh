@@ -1,0 +1,416 @@
+// mf_inflate.cuh -- INFLATE + CRC-32 verification kernels for sm_100a.
+//
+// Replaces ContentAddressedStore._unpack_v1 (metaflow/datastore/content_addressed_store.py:218-220:
+// gzip.GzipFile(mode="rb").read() -> zlib inflate, CRC-32 / ISIZE check gzip.py:550-566).
+//
+//   mf_parse_kernel          one warp per blob: walk the RFC 1952 members; 'MF'-indexed members are
+//                            expanded into chunk descriptors, anything else is flagged "foreign"
+//   mf_inflate_chunk_kernel  one warp per 32 KiB chunk, one LANE per 1 KiB segment: lane 0 parses the
+//                            block header, the warp builds lookup tables with match.any ranks, then
+//                            32 lanes Huffman-decode 32 segments concurrently (the index gives every
+//                            segment's bit offset; LZ77 matches never leave a segment), output staged
+//                            in padded shared-memory rows, CRC-32 per lane, coalesced stores to HBM
+//   mf_verify_kernel         one warp per member: GF(2)-combine the chunk CRCs, compare with trailer
+//   mf_gunzip_lane_kernel    foreign streams (stock Metaflow / zlib level 3 writers): a DEFLATE stream
+//                            without an index is bit-serial, so one lane decodes one whole blob
+#pragma once
+#include <cuda_runtime.h>
+#include "mf_core.h"
+#include "mf_inflate_core.h"
+#include "mf_deflate.cuh"   // g_mf_crc_tab, g_mf_piece_mul, warp helpers
+
+struct MfDecBlob {
+    const uint8_t *src; uint64_t src_len;
+    uint8_t *dst; uint64_t dst_cap;
+};
+struct MfDecChunk {
+    const uint8_t *src;       // first byte of the chunk's DEFLATE block
+    const uint8_t *segidx;    // 32 little-endian u16 segment bit lengths (unaligned)
+    uint8_t *dst;
+    uint32_t comp_bytes;
+    uint32_t raw_len;         // 1..32768
+    uint32_t hdr_bits;        // MF_STORED_MARK for a stored chunk
+    uint32_t blob;
+};
+struct MfDecMember {
+    uint32_t blob, raw_len, crc_expect, first_chunk, n_chunks;
+};
+struct MfDecCounters { uint32_t n_chunks, n_members; };
+
+__device__ __forceinline__ void mf_set_status(int32_t *status, uint32_t blob, int32_t err) { atomicCAS(&status[blob], 0, err); }
+
+// kind[b]: 0 = indexed (chunks emitted), 1 = foreign (lane decoder), 2 = failed in parse
+__global__ void __launch_bounds__(32)
+mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChunk *__restrict__ chunks, uint32_t max_chunks,
+                MfDecMember *__restrict__ members, uint32_t max_members, MfDecCounters *__restrict__ counters,
+                uint8_t *__restrict__ kind, uint64_t *__restrict__ dst_len, int32_t *__restrict__ status) {
+    const uint32_t b = blockIdx.x, lane = threadIdx.x;
+    if (b >= n_blobs) return;
+    const MfDecBlob blob = blobs[b];
+    const uint8_t *src = blob.src;
+    const uint64_t n = blob.src_len;
+    // pass A (lane 0): walk the members, check structure, total size
+    int verdict = 0;      // 0 indexed ok, 1 foreign, >1: error code + 16
+    uint64_t total = 0;
+    uint32_t nmem = 0, nch = 0;
+    if (lane == 0) {
+        uint64_t ip = 0;
+        while (ip < n) {
+            if (nmem) { while (ip < n && src[ip] == 0) ip++; if (ip >= n) break; }
+            uint32_t rl, nc;
+            uint64_t hdr = mf_is_indexed_member(src + ip, n - ip, &rl, &nc);
+            if (!hdr) { verdict = 1; break; }
+            uint64_t payload = 0;
+            for (uint32_t k = 0; k < nc; k++) payload += mf_le32(src + ip + MF_HDR_FIXED + 8ull * k);
+            if (ip + hdr + payload + MF_TRAILER > n) { verdict = 16 + MF_DEC_E_TRUNC; break; }
+            const uint8_t *t = src + ip + hdr + payload;
+            if (t[0] != 1 || t[1] != 0 || t[2] != 0 || t[3] != 0xFF || t[4] != 0xFF) { verdict = 1; break; }
+            if (mf_le32(t + 9) != rl) { verdict = 16 + MF_DEC_E_ISIZE; break; }
+            total += rl; nmem++; nch += nc;
+            ip += hdr + payload + MF_TRAILER;
+        }
+        if (verdict == 0 && nmem == 0) verdict = 16 + MF_DEC_E_TRUNC;
+    }
+    verdict = __shfl_sync(0xFFFFFFFFu, verdict, 0);
+    total = __shfl_sync(0xFFFFFFFFu, total, 0);
+    nmem = __shfl_sync(0xFFFFFFFFu, nmem, 0);
+    nch = __shfl_sync(0xFFFFFFFFu, nch, 0);
+    if (verdict == 1) { if (lane == 0) { kind[b] = 1; } return; }
+    if (verdict >= 16) { if (lane == 0) { kind[b] = 2; status[b] = verdict - 16; dst_len[b] = 0; } return; }
+    if (total > blob.dst_cap) { if (lane == 0) { kind[b] = 2; status[b] = MF_DEC_E_DST; dst_len[b] = total; } return; }
+    uint32_t cbase = 0, mbase = 0;
+    if (lane == 0) { cbase = atomicAdd(&counters->n_chunks, nch); mbase = atomicAdd(&counters->n_members, nmem); }
+    cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+    mbase = __shfl_sync(0xFFFFFFFFu, mbase, 0);
+    if (cbase + nch > max_chunks || mbase + nmem > max_members) { if (lane == 0) kind[b] = 1; return; }   // let the lane decoder take it
+    if (lane == 0) { kind[b] = 0; dst_len[b] = total; }
+    // pass B (whole warp): emit descriptors
+    uint64_t ip = 0, op = 0;
+    for (uint32_t mi = 0; mi < nmem; mi++) {
+        while (src[ip] == 0) ip++;       // padding (structure validated above)
+        const uint8_t *h = src + ip;
+        const uint32_t rl = mf_le32(h + 20), nc = mf_le32(h + 24);
+        const uint32_t hdr = mf_member_header_bytes(nc);
+        const uint32_t per = (nc + 31u) / 32u;
+        uint32_t mine = 0;
+        for (uint32_t k = 0; k < per; k++) { uint32_t ch = lane * per + k; if (ch < nc) mine += mf_le32(h + MF_HDR_FIXED + 8ull * ch); }
+        uint32_t incl = mf_warp_incl_scan(mine, lane);
+        uint32_t run = incl - mine;
+        const uint32_t payload = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        for (uint32_t k = 0; k < per; k++) {
+            uint32_t ch = lane * per + k;
+            if (ch >= nc) break;
+            const uint8_t *e = h + MF_HDR_FIXED + 8ull * ch;
+            MfDecChunk d;
+            d.comp_bytes = mf_le32(e);
+            d.hdr_bits = mf_le16(e + 4);
+            d.src = h + hdr + run;
+            d.segidx = h + MF_HDR_FIXED + 8ull * nc + 64ull * ch;
+            d.dst = blob.dst + op + (uint64_t)ch * MF_CHUNK;
+            d.raw_len = min((uint32_t)MF_CHUNK, rl - ch * MF_CHUNK);
+            d.blob = b;
+            chunks[cbase + ch] = d;
+            run += d.comp_bytes;
+        }
+        if (lane == 0) {
+            MfDecMember m;
+            m.blob = b; m.raw_len = rl; m.first_chunk = cbase; m.n_chunks = nc;
+            m.crc_expect = mf_le32(h + hdr + payload + 5);
+            members[mbase + mi] = m;
+        }
+        cbase += nc;
+        ip += (uint64_t)hdr + payload + MF_TRAILER;
+        op += rl;
+    }
+}
+
+// ------------------------------------------------------------------ chunk decoder
+#define MF_DEC_WARPS 2
+#define MF_ROW (MF_SEG + 4u)          // padded row: lanes writing the same column hit distinct banks
+#define MF_LL_LUT_BITS 10
+#define MF_D_LUT_BITS 8
+
+struct MfCanonSmall { uint16_t count[16]; uint16_t symbol[32]; };
+
+struct __align__(16) MfDecWarpSmem {
+    uint8_t out[MF_SEGS_PER_CHUNK * MF_ROW];
+    uint16_t lut_ll[1u << MF_LL_LUT_BITS];   // sym | len << 9 ; 0 = code longer than the LUT
+    uint16_t lut_d[1u << MF_D_LUT_BITS];     // sym | len << 5
+    uint8_t lens[320];
+    MfCanon ll;
+    MfCanonSmall dd;
+    uint32_t cnt_ll[16], cnt_d[16];
+    uint32_t next_ll[16], next_d[16];        // running canonical code per length
+    uint32_t offs_ll[16], offs_d[16];        // running sorted-symbol slot per length
+    int32_t err;
+    uint32_t hlit, hdist, hdr_end;
+};
+struct __align__(16) MfDecSmem {
+    uint32_t crc_tab[256];
+    MfDecWarpSmem w[MF_DEC_WARPS];
+};
+
+struct MfFastReader {
+    const uint32_t *w;
+    uint64_t buf;
+    uint32_t cnt;
+    uint64_t used;   // bits consumed since init
+    __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos) {
+        const uint8_t *a = src + (bitpos >> 3);
+        uintptr_t al = (uintptr_t)a & ~(uintptr_t)3;
+        uint32_t skip = (uint32_t)((uintptr_t)a - al) * 8u + (uint32_t)(bitpos & 7u);
+        w = reinterpret_cast<const uint32_t *>(al);
+        buf = (uint64_t)__ldg(w++) >> skip;
+        cnt = 32u - skip;
+        buf |= (uint64_t)__ldg(w++) << cnt; cnt += 32u;
+        used = 0;
+    }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)__ldg(w++) << cnt; cnt += 32u; } }
+    __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }   // k <= 16, call fill() first
+    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; used += k; }
+    __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
+};
+
+__device__ __forceinline__ int mf_canon_decode_fast(MfFastReader &br, const uint16_t *count, const uint16_t *symbol) {
+    uint32_t bits = (uint32_t)br.buf;
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)(bits & 1u); bits >>= 1;
+        int cnt = count[l];
+        if (code - cnt < first) { br.drop((uint32_t)l); return symbol[index + (code - first)]; }
+        index += cnt; first += cnt; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(32 * MF_DEC_WARPS)
+mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounters *__restrict__ counters,
+                        uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status) {
+    extern __shared__ __align__(16) uint8_t mf_smem_raw[];
+    MfDecSmem &S = *reinterpret_cast<MfDecSmem *>(mf_smem_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) S.crc_tab[i] = g_mf_crc_tab[0][i];
+    __syncthreads();
+    const uint32_t c = blockIdx.x * MF_DEC_WARPS + warp;
+    if (c >= counters->n_chunks) return;
+    MfDecWarpSmem &W = S.w[warp];
+    const MfDecChunk ch = chunks[c];
+    const uint32_t raw_len = ch.raw_len;
+    int err = 0;
+
+    if (ch.hdr_bits == MF_STORED_MARK) {
+        // 00 | LEN | NLEN | raw bytes
+        if (lane == 0) {
+            const uint8_t *p = ch.src;
+            uint32_t len = p[1] | ((uint32_t)p[2] << 8), nlen = p[3] | ((uint32_t)p[4] << 8);
+            if ((p[0] & 7u) != 0 || len != (raw_len & 0xFFFFu) || (len ^ 0xFFFFu) != nlen || ch.comp_bytes != raw_len + 5u) W.err = MF_DEC_E_STREAM;
+            else W.err = 0;
+        }
+        __syncwarp();
+        err = W.err;
+        if (!err) {
+            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
+                uint32_t base = r * MF_SEG;
+                for (uint32_t k = lane; k < MF_SEG && base + k < raw_len; k += 32) W.out[r * MF_ROW + k] = ch.src[5u + base + k];
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- block header (lane 0), lengths into smem
+        if (lane == 0) {
+            MfBitReader br; br.init(ch.src, ch.comp_bytes, 0);
+            uint32_t bfinal = br.get(1), btype = br.get(2);
+            int e = 0;
+            uint32_t hlit = 0, hdist = 0;
+            if (bfinal != 0 || btype != 2) e = MF_DEC_E_STREAM;
+            if (!e) e = mf_read_dynamic_tables(br, W.lens, hlit, hdist);
+            if (!e && br.bitpos() != ch.hdr_bits) e = MF_DEC_E_STREAM;
+            W.err = e; W.hlit = hlit; W.hdist = hdist;
+        }
+        for (uint32_t i = lane; i < (1u << MF_LL_LUT_BITS); i += 32) W.lut_ll[i] = 0;
+        for (uint32_t i = lane; i < (1u << MF_D_LUT_BITS); i += 32) W.lut_d[i] = 0;
+        if (lane < 16) { W.cnt_ll[lane] = 0; W.cnt_d[lane] = 0; }
+        __syncwarp();
+        err = W.err;
+        if (!err) {
+            const uint32_t hlit = W.hlit, hdist = W.hdist;
+            // counts per length
+            for (uint32_t s = lane; s < hlit; s += 32) { uint32_t l = W.lens[s]; if (l) atomicAdd(&W.cnt_ll[l], 1u); }
+            for (uint32_t s = lane; s < hdist; s += 32) { uint32_t l = W.lens[hlit + s]; if (l) atomicAdd(&W.cnt_d[l], 1u); }
+            __syncwarp();
+            if (lane < 2) {
+                uint32_t *cnt = lane ? W.cnt_d : W.cnt_ll, *next = lane ? W.next_d : W.next_ll, *offs = lane ? W.offs_d : W.offs_ll;
+                uint32_t code = 0, off = 0, used = 0;
+                int left = 1;
+                cnt[0] = 0;
+                for (int l = 1; l < 16; l++) {
+                    code = (code + cnt[l - 1]) << 1; next[l] = code;
+                    offs[l] = off; off += cnt[l]; used += cnt[l];
+                    left = (left << 1) - (int)cnt[l];
+                    if (left < 0) break;
+                }
+                // over-subscribed, or incomplete with more than one code (RFC 1951 allows a single-code tree)
+                if (left < 0 || (left > 0 && used > 1) || (lane == 0 && used == 0)) W.err = MF_DEC_E_STREAM;
+                uint16_t *cc = lane ? W.dd.count : W.ll.count;
+                for (int l = 0; l < 16; l++) cc[l] = (uint16_t)cnt[l];
+            }
+            __syncwarp();
+            err = W.err;
+        }
+        if (!err) {
+            const uint32_t hlit = W.hlit, hdist = W.hdist;
+            // canonical code of every symbol: next[len] + rank among equal lengths (match.any gives the rank)
+            for (uint32_t base = 0; base < 288; base += 32) {
+                uint32_t s = base + lane;
+                uint32_t l = (s < hlit) ? W.lens[s] : 0u;
+                uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
+                uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                uint32_t code = 0, slot = 0;
+                if (l) { code = W.next_ll[l] + rank; slot = W.offs_ll[l] + rank; }
+                __syncwarp();
+                if (l && rank == 0) { W.next_ll[l] += __popc(peers); W.offs_ll[l] += __popc(peers); }
+                __syncwarp();
+                if (l) {
+                    W.ll.symbol[slot] = (uint16_t)s;
+                    if (l <= MF_LL_LUT_BITS) {
+                        uint32_t rev = __brev(code) >> (32 - l);
+                        uint16_t e = (uint16_t)(s | (l << 9));
+                        for (uint32_t k = rev; k < (1u << MF_LL_LUT_BITS); k += (1u << l)) W.lut_ll[k] = e;
+                    }
+                }
+            }
+            {
+                uint32_t s = lane;
+                uint32_t l = (s < hdist) ? W.lens[hlit + s] : 0u;
+                uint32_t peers = __match_any_sync(0xFFFFFFFFu, l);
+                uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                if (l) {
+                    uint32_t code = W.next_d[l] + rank;
+                    W.dd.symbol[W.offs_d[l] + rank] = (uint16_t)s;
+                    if (l <= MF_D_LUT_BITS) {
+                        uint32_t rev = __brev(code) >> (32 - l);
+                        uint16_t e = (uint16_t)(s | (l << 5));
+                        for (uint32_t k = rev; k < (1u << MF_D_LUT_BITS); k += (1u << l)) W.lut_d[k] = e;
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- 32 lanes decode 32 segments
+            const uint32_t mybits = mf_le16(ch.segidx + 2u * lane);
+            const uint32_t incl = mf_warp_incl_scan(mybits, lane);
+            const uint32_t seg_base = lane * MF_SEG;
+            int lerr = 0;
+            const uint32_t allbits = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            if ((uint64_t)ch.hdr_bits + allbits > (uint64_t)ch.comp_bytes * 8ull) lerr = MF_DEC_E_STREAM;   // index points past the chunk
+            else if (seg_base < raw_len) {
+                const uint32_t seglen = min((uint32_t)MF_SEG, raw_len - seg_base);
+                uint8_t *row = W.out + lane * MF_ROW;
+                MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits);
+                uint32_t op = 0;
+                while (op < seglen) {
+                    if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
+                    br.fill();
+                    uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
+                    int sym;
+                    if (e) { sym = (int)(e & 511u); br.drop(e >> 9); }
+                    else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
+                    if (sym < 256) { row[op++] = (uint8_t)sym; continue; }
+                    if (sym == 256 || sym > 285) { lerr = MF_DEC_E_STREAM; break; }
+                    br.fill();
+                    sym -= 257;
+                    uint32_t len = mf_lbase(sym) + br.get(mf_lext(sym));
+                    br.fill();
+                    uint32_t de = W.lut_d[br.peek(MF_D_LUT_BITS)];
+                    int ds;
+                    if (de) { ds = (int)(de & 31u); br.drop(de >> 5); }
+                    else { ds = mf_canon_decode_fast(br, W.dd.count, W.dd.symbol); if (ds < 0) { lerr = MF_DEC_E_STREAM; break; } }
+                    if (ds >= 30) { lerr = MF_DEC_E_STREAM; break; }
+                    br.fill();
+                    uint32_t dist = mf_dbase(ds) + br.get(mf_dext(ds));
+                    if (dist > op || op + len > seglen) { lerr = MF_DEC_E_STREAM; break; }
+                    for (uint32_t k = 0; k < len; k++) { row[op] = row[op - dist]; op++; }
+                }
+                if (!lerr && br.used != mybits) lerr = MF_DEC_E_STREAM;
+            } else if (mybits != 0) lerr = MF_DEC_E_STREAM;
+            if (__any_sync(0xFFFFFFFFu, lerr != 0)) err = MF_DEC_E_STREAM;
+        }
+        __syncwarp();
+    }
+    if (err) { if (lane == 0) { mf_set_status(status, ch.blob, err); chunk_crc[c] = 0; } return; }
+
+    // ---- CRC-32 of the chunk: one 1 KiB row per lane, then GF(2) shift + xor-reduce
+    {
+        const uint32_t seg_base = lane * MF_SEG;
+        uint32_t crc = 0;
+        if (seg_base < raw_len) {
+            const uint32_t seglen = min((uint32_t)MF_SEG, raw_len - seg_base);
+            const uint8_t *row = W.out + lane * MF_ROW;
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
+            uint32_t nw = seglen >> 2;
+            for (uint32_t i = 0; i < nw; i++) {
+                uint32_t x = rw[i];
+                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
+                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
+                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
+                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8);
+            }
+            for (uint32_t p = nw << 2; p < seglen; p++) crc = S.crc_tab[(crc ^ row[p]) & 0xFFu] ^ (crc >> 8);
+            uint32_t after = raw_len - (seg_base + seglen);
+            uint32_t mul = ((after & 63u) == 0) ? g_mf_piece_mul[after >> 6] : mf_xpow8(after);
+            crc = mf_gf2_mul(crc, mul);
+        }
+        crc = mf_warp_xor(crc);
+        if (lane == 0) chunk_crc[c] = crc;
+    }
+    // ---- rows -> HBM
+    {
+        uint8_t *dst = ch.dst;
+        if (((uintptr_t)dst & 3u) == 0) {
+            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
+                uint32_t base = r * MF_SEG;
+                if (base >= raw_len) break;
+                uint32_t seglen = min((uint32_t)MF_SEG, raw_len - base);
+                const uint32_t *rw = reinterpret_cast<const uint32_t *>(W.out + r * MF_ROW);
+                uint32_t *dw = reinterpret_cast<uint32_t *>(dst + base);
+                uint32_t nw = seglen >> 2;
+                for (uint32_t i = lane; i < nw; i += 32) dw[i] = rw[i];
+                uint32_t tail = seglen & 3u;
+                if (lane < tail) dst[base + (nw << 2) + lane] = W.out[r * MF_ROW + (nw << 2) + lane];
+            }
+        } else {
+            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
+                uint32_t base = r * MF_SEG;
+                for (uint32_t k = lane; k < MF_SEG && base + k < raw_len; k += 32) dst[base + k] = W.out[r * MF_ROW + k];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128)
+mf_verify_kernel(const MfDecMember *__restrict__ members, const MfDecCounters *__restrict__ counters,
+                 const uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (m >= counters->n_members) return;
+    const MfDecMember mem = members[m];
+    uint32_t acc = 0;
+    for (uint32_t k = lane; k < mem.n_chunks; k += 32) {
+        uint64_t chunk_end = min((uint64_t)(k + 1) * MF_CHUNK, (uint64_t)mem.raw_len);
+        acc ^= mf_gf2_mul(chunk_crc[mem.first_chunk + k], mf_xpow8((uint64_t)mem.raw_len - chunk_end));
+    }
+    acc = mf_warp_xor(acc);
+    if (lane == 0 && mf_crc_finish(acc, mem.raw_len) != mem.crc_expect) mf_set_status(status, mem.blob, MF_DEC_E_CRC);
+}
+
+// foreign streams: one lane per blob
+__global__ void __launch_bounds__(64)
+mf_gunzip_lane_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, const uint8_t *__restrict__ kind,
+                      uint64_t *__restrict__ dst_len, int32_t *__restrict__ status) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blobs || kind[b] != 1) return;
+    const MfDecBlob blob = blobs[b];
+    uint64_t produced = 0;
+    int e = mf_gunzip_stream(blob.src, blob.src_len, blob.dst, blob.dst_cap, &produced, &g_mf_crc_tab[0][0]);
+    status[b] = e;
+    dst_len[b] = e ? 0 : produced;
+}

@@ -1,0 +1,574 @@
+// mfcas.cu -- host runtime and C ABI (include/mfcas.h) of the B200 artifact codec.
+//
+// The batcher side of the design: a batch of blobs (one foreach step's artifact set) is sharded
+// round-robin over the context's GPUs (blob i -> device i mod G; independent blobs, no collective),
+// each shard is cut into waves that fit the device arena, and every wave runs
+//   H2D (cudaMemcpyAsync, coalesced over contiguous host ranges) -> kernels -> D2H
+// on the device's streams.  This replaces the reference's process-per-task parallelism
+// (metaflow/runtime.py:1517-1540) and multicore_utils.parallel_map (metaflow/multicore_utils.py:140-175)
+// for the artifact work.  There is no CPU implementation of the path in this library.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mfcas.h"
+#include "mf_core.h"
+#include "mf_sha1.cuh"
+#include "mf_deflate.cuh"
+#include "mf_inflate.cuh"
+
+#define MFCAS_VERSION_STR "mfcas 0.1 (sm_100a; format MF v1: chunk 32 KiB, segment 1 KiB)"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {     // pinned
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+struct DeviceState {
+    int dev = -1;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_in = nullptr, ev_sha = nullptr;
+    // wave arenas (host-pointer API)
+    DevBuf in_arena, out_arena;
+    // descriptors / results
+    DevBuf d_desc, d_work, slots;
+    HostBuf h_desc, h_res;
+    std::string err;
+    uint64_t launches = 0, h2d = 0, d2h = 0;
+    float ms[8] = {};
+};
+
+}  // namespace
+
+struct mfcas_ctx {
+    std::vector<DeviceState> devs;
+    uint64_t wave_bytes = 1ull << 30;
+    uint32_t flags = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            char _b[512];                                                                            \
+            snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            D.err = _b;                                                                              \
+            (void)cudaGetLastError();                                                                \
+            return MFCAS_E_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+// carve helper over one contiguous buffer
+struct Carver {
+    size_t off = 0;
+    size_t take(size_t bytes, size_t align = 256) { off = align_up(off, align); size_t o = off; off += bytes; return o; }
+};
+
+int device_setup(DeviceState &D) {
+    CU(cudaSetDevice(D.dev));
+    CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking));
+    for (auto &e : D.ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&D.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&D.ev_sha, cudaEventDisableTiming));
+    CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
+    CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
+    mf_init_tables_kernel<<<2, 256, 0, D.stream>>>();
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(D.stream));
+    return MFCAS_OK;
+}
+
+void device_teardown(DeviceState &D) {
+    if (D.dev < 0) return;
+    cudaSetDevice(D.dev);
+    if (D.stream) cudaStreamSynchronize(D.stream);
+    if (D.stream2) cudaStreamSynchronize(D.stream2);
+    D.in_arena.release(); D.out_arena.release(); D.d_desc.release(); D.d_work.release(); D.slots.release();
+    D.h_desc.release(); D.h_res.release();
+    for (auto &e : D.ev) if (e) cudaEventDestroy(e);
+    if (D.ev_in) cudaEventDestroy(D.ev_in);
+    if (D.ev_sha) cudaEventDestroy(D.ev_sha);
+    if (D.stream) cudaStreamDestroy(D.stream);
+    if (D.stream2) cudaStreamDestroy(D.stream2);
+}
+
+// ------------------------------------------------------------------ device-resident pack
+// want_pack == false: hash only.
+int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                   void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status,
+                   bool want_pack, bool inputs_on_stream) {
+    if (n == 0) return MFCAS_OK;
+    if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
+    CU(cudaSetDevice(D.dev));
+    // ---- host-side descriptors
+    uint64_t n_members = 0, n_chunks = 0;
+    if (want_pack)
+        for (uint64_t i = 0; i < n; i++) { n_members += mf_n_members(src_len[i]); n_chunks += mf_n_chunks(src_len[i]); }
+    if (n_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
+    Carver hc;
+    const size_t o_hash = hc.take(sizeof(MfHashDesc) * n);
+    const size_t o_blob = hc.take(sizeof(MfEncBlob) * n);
+    const size_t o_mem = hc.take(sizeof(MfEncMember) * n_members);
+    const size_t o_cm = hc.take(sizeof(uint32_t) * n_chunks);
+    const size_t desc_bytes = hc.take(0);
+    CU(D.h_desc.ensure(desc_bytes));
+    CU(D.d_desc.ensure(desc_bytes));
+    uint8_t *hd = D.h_desc.as<uint8_t>();
+    MfHashDesc *h_hash = reinterpret_cast<MfHashDesc *>(hd + o_hash);
+    MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
+    MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
+    uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
+    uint32_t mi = 0, ci = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        h_hash[i].src = static_cast<const uint8_t *>(d_src[i]);
+        h_hash[i].len = src_len[i];
+        if (!want_pack) continue;
+        h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
+        h_blob[i].dst_cap = dst_cap[i];
+        h_blob[i].first_member = mi;
+        uint64_t nm = mf_n_members(src_len[i]);
+        h_blob[i].n_members = (uint32_t)nm;
+        for (uint64_t m = 0; m < nm; m++) {
+            uint64_t off = m * MF_MEMBER_RAW;
+            uint64_t rl = std::min<uint64_t>(MF_MEMBER_RAW, src_len[i] - off);
+            MfEncMember &M = h_mem[mi];
+            M.src = static_cast<const uint8_t *>(d_src[i]) + off;
+            M.raw_len = (uint32_t)rl;
+            M.n_chunks = (uint32_t)mf_n_chunks(rl);
+            M.first_chunk = ci;
+            M.blob = (uint32_t)i;
+            for (uint32_t k = 0; k < M.n_chunks; k++) h_cm[ci++] = mi;
+            mi++;
+        }
+    }
+    // ---- device work buffers
+    Carver wc;
+    const size_t o_comp = wc.take(sizeof(uint32_t) * n_chunks);
+    const size_t o_hdr = wc.take(sizeof(uint16_t) * n_chunks);
+    const size_t o_seg = wc.take(sizeof(uint16_t) * n_chunks * MF_SEGS_PER_CHUNK);
+    const size_t o_crc = wc.take(sizeof(uint32_t) * n_chunks);
+    const size_t o_cdst = wc.take(sizeof(uint64_t) * n_chunks);
+    const size_t o_res = wc.take(0);                       // results block, mirrored to the host
+    Carver rc;
+    const size_t r_len = rc.take(sizeof(uint64_t) * n, 16);
+    const size_t r_st = rc.take(sizeof(int32_t) * n, 16);
+    const size_t r_sha = rc.take(20 * n, 16);
+    const size_t res_bytes = rc.take(0, 16);
+    CU(D.d_work.ensure(o_res + res_bytes));
+    CU(D.h_res.ensure(res_bytes));
+    if (want_pack) CU(D.slots.ensure((size_t)n_chunks * MF_SLOT + 64));
+    uint8_t *dw = D.d_work.as<uint8_t>();
+    uint8_t *dd = D.d_desc.as<uint8_t>();
+    uint8_t *dres = dw + o_res;
+
+    cudaStream_t s = D.stream, s2 = D.stream2;
+    CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(dres + r_st, 0, sizeof(int32_t) * n, s));
+    CU(cudaEventRecord(D.ev_in, s));
+    (void)inputs_on_stream;
+    // ---- SHA-1 on the second stream (serial per blob, so it overlaps the chunk-parallel encoder)
+    CU(cudaStreamWaitEvent(s2, D.ev_in, 0));
+    CU(cudaEventRecord(D.ev[0], s2));
+    mf_sha1_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
+    CU(cudaGetLastError());
+    D.launches++;
+    CU(cudaEventRecord(D.ev[1], s2));
+    CU(cudaEventRecord(D.ev_sha, s2));
+    if (want_pack) {
+        CU(cudaEventRecord(D.ev[2], s));
+        if (n_chunks) {
+            mf_deflate_kernel<<<(unsigned)n_chunks, MF_ENC_THREADS, sizeof(MfEncSmem), s>>>(
+                reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
+                D.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
+                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags);
+            CU(cudaGetLastError());
+            D.launches++;
+        }
+        CU(cudaEventRecord(D.ev[3], s));
+        mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, s>>>(
+            reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
+            reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint16_t *>(dw + o_hdr),
+            reinterpret_cast<const uint16_t *>(dw + o_seg), reinterpret_cast<const uint32_t *>(dw + o_crc),
+            reinterpret_cast<uint64_t *>(dw + o_cdst), reinterpret_cast<uint64_t *>(dres + r_len), reinterpret_cast<int32_t *>(dres + r_st));
+        CU(cudaGetLastError());
+        D.launches++;
+        if (n_chunks) {
+            mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(
+                reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
+                reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, D.slots.as<uint8_t>(),
+                reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint64_t *>(dw + o_cdst));
+            CU(cudaGetLastError());
+            D.launches++;
+        }
+        CU(cudaEventRecord(D.ev[4], s));
+    }
+    CU(cudaStreamWaitEvent(s, D.ev_sha, 0));
+    CU(cudaMemcpyAsync(D.h_res.p, dres, res_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint8_t *hr = D.h_res.as<uint8_t>();
+    if (sha1) memcpy(sha1, hr + r_sha, 20 * n);
+    if (want_pack) {
+        memcpy(dst_len, hr + r_len, sizeof(uint64_t) * n);
+        memcpy(status, hr + r_st, sizeof(int32_t) * n);
+        cudaEventElapsedTime(&D.ms[1], D.ev[2], D.ev[3]);
+        cudaEventElapsedTime(&D.ms[2], D.ev[3], D.ev[4]);
+    } else if (status) {
+        for (uint64_t i = 0; i < n; i++) status[i] = 0;
+    }
+    cudaEventElapsedTime(&D.ms[0], D.ev[0], D.ev[1]);
+    return MFCAS_OK;
+}
+
+// ------------------------------------------------------------------ device-resident unpack
+int unpack_on_device(DeviceState &D, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                     void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, int32_t *status) {
+    if (n == 0) return MFCAS_OK;
+    if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
+    CU(cudaSetDevice(D.dev));
+    uint64_t max_chunks = 0, max_members = 0;
+    for (uint64_t i = 0; i < n; i++) { max_chunks += dst_cap[i] / MF_CHUNK + 1; max_members += dst_cap[i] / MF_MEMBER_RAW + 2; }
+    if (max_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
+    CU(D.h_desc.ensure(sizeof(MfDecBlob) * n));
+    MfDecBlob *hb = D.h_desc.as<MfDecBlob>();
+    for (uint64_t i = 0; i < n; i++) {
+        hb[i].src = static_cast<const uint8_t *>(d_src[i]); hb[i].src_len = src_len[i];
+        hb[i].dst = static_cast<uint8_t *>(d_dst[i]); hb[i].dst_cap = dst_cap[i];
+    }
+    CU(D.d_desc.ensure(sizeof(MfDecBlob) * n));
+    Carver wc;
+    const size_t o_chunks = wc.take(sizeof(MfDecChunk) * max_chunks);
+    const size_t o_members = wc.take(sizeof(MfDecMember) * max_members);
+    const size_t o_crc = wc.take(sizeof(uint32_t) * max_chunks);
+    const size_t o_kind = wc.take(n);
+    const size_t o_cnt = wc.take(sizeof(MfDecCounters));
+    const size_t o_res = wc.take(0);
+    Carver rc;
+    const size_t r_len = rc.take(sizeof(uint64_t) * n, 16);
+    const size_t r_st = rc.take(sizeof(int32_t) * n, 16);
+    const size_t res_bytes = rc.take(0, 16);
+    CU(D.d_work.ensure(o_res + res_bytes));
+    CU(D.h_res.ensure(res_bytes));
+    uint8_t *dw = D.d_work.as<uint8_t>();
+    uint8_t *dres = dw + o_res;
+    cudaStream_t s = D.stream;
+    CU(cudaMemcpyAsync(D.d_desc.p, hb, sizeof(MfDecBlob) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + res_bytes) - o_kind, s));     // kind, counters, dst_len, status
+    const MfDecBlob *db = D.d_desc.as<MfDecBlob>();
+    MfDecCounters *cnt = reinterpret_cast<MfDecCounters *>(dw + o_cnt);
+    CU(cudaEventRecord(D.ev[5], s));
+    mf_parse_kernel<<<(unsigned)n, 32, 0, s>>>(db, (uint32_t)n, reinterpret_cast<MfDecChunk *>(dw + o_chunks), (uint32_t)max_chunks,
+                                               reinterpret_cast<MfDecMember *>(dw + o_members), (uint32_t)max_members, cnt,
+                                               dw + o_kind, reinterpret_cast<uint64_t *>(dres + r_len), reinterpret_cast<int32_t *>(dres + r_st));
+    CU(cudaGetLastError());
+    mf_inflate_chunk_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS - 1) / MF_DEC_WARPS), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
+        reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + r_st));
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(D.ev[6], s));
+    mf_verify_kernel<<<(unsigned)((max_members * 32 + 127) / 128), 128, 0, s>>>(
+        reinterpret_cast<const MfDecMember *>(dw + o_members), cnt, reinterpret_cast<const uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + r_st));
+    CU(cudaGetLastError());
+    mf_gunzip_lane_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + r_len),
+                                                                  reinterpret_cast<int32_t *>(dres + r_st));
+    CU(cudaGetLastError());
+    D.launches += 4;
+    CU(cudaEventRecord(D.ev[7], s));
+    CU(cudaMemcpyAsync(D.h_res.p, dres, res_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    const uint8_t *hr = D.h_res.as<uint8_t>();
+    memcpy(dst_len, hr + r_len, sizeof(uint64_t) * n);
+    memcpy(status, hr + r_st, sizeof(int32_t) * n);
+    cudaEventElapsedTime(&D.ms[3], D.ev[5], D.ev[6]);
+    cudaEventElapsedTime(&D.ms[4], D.ev[6], D.ev[7]);
+    return MFCAS_OK;
+}
+
+// ------------------------------------------------------------------ host-pointer shards (waves)
+enum class Op { Pack, Hash, Unpack };
+
+struct Shard {
+    std::vector<uint64_t> idx;     // blob indices of this device, in order
+};
+
+// Copies a set of (host ptr, device ptr, len) with runs of contiguous pairs merged into one memcpy.
+struct CopyPlan {
+    struct Item { char *h; char *d; size_t n; };
+    std::vector<Item> items;
+    void add(const void *h, void *d, size_t n) {
+        if (!n) return;
+        char *hc = (char *)h, *dc = (char *)d;
+        if (!items.empty()) {
+            Item &l = items.back();
+            ptrdiff_t gh = hc - l.h, gd = dc - l.d;
+            // same displacement on both sides and the gap after the previous item is small: extend
+            if (gh == gd && gh >= (ptrdiff_t)l.n && gh - (ptrdiff_t)l.n <= 4096) { l.n = (size_t)gh + n; return; }
+        }
+        items.push_back({hc, dc, n});
+    }
+};
+
+int run_shard(mfcas_ctx *ctx, DeviceState &D, Op op, const Shard &sh,
+              const void *const *src, const uint64_t *src_len, void *const *dst, const uint64_t *dst_cap,
+              uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+    const uint64_t wave_bytes = ctx->wave_bytes;
+    size_t pos = 0;
+    std::vector<const void *> w_src; std::vector<void *> w_dst;
+    std::vector<uint64_t> w_len, w_cap, w_dlen, w_ioff, w_ooff;
+    std::vector<int32_t> w_st; std::vector<uint8_t> w_sha;
+    CU(cudaSetDevice(D.dev));
+    while (pos < sh.idx.size()) {
+        // ---- choose the wave: blobs until the staged bytes (in + out) exceed wave_bytes
+        size_t end = pos; uint64_t in_bytes = 0, out_bytes = 0;
+        w_ioff.clear(); w_ooff.clear(); w_cap.clear();
+        while (end < sh.idx.size()) {
+            uint64_t i = sh.idx[end];
+            uint64_t il = align_up(src_len[i], 256) + 256;
+            uint64_t oc = 0;
+            if (op == Op::Pack) oc = std::min<uint64_t>(mf_pack_bound(src_len[i]), dst_cap[i]);
+            else if (op == Op::Unpack) oc = dst_cap[i];
+            uint64_t ol = align_up(oc, 256) + 256;
+            if (end > pos && in_bytes + il + out_bytes + ol > wave_bytes) break;
+            w_ioff.push_back(in_bytes); w_ooff.push_back(out_bytes); w_cap.push_back(oc);
+            in_bytes += il; out_bytes += ol; end++;
+        }
+        const size_t wn = end - pos;
+        CU(D.in_arena.ensure(in_bytes + 256));
+        if (op != Op::Hash) CU(D.out_arena.ensure(out_bytes + 256));
+        // ---- H2D
+        CopyPlan up;
+        w_src.resize(wn); w_dst.resize(wn); w_len.resize(wn); w_dlen.assign(wn, 0); w_st.assign(wn, 0); w_sha.resize(20 * wn);
+        for (size_t k = 0; k < wn; k++) {
+            uint64_t i = sh.idx[pos + k];
+            w_src[k] = D.in_arena.as<char>() + w_ioff[k];
+            w_dst[k] = (op == Op::Hash) ? nullptr : (void *)(D.out_arena.as<char>() + w_ooff[k]);
+            w_len[k] = src_len[i];
+            up.add(src[i], (void *)w_src[k], src_len[i]);
+        }
+        for (auto &it : up.items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, D.stream)); D.h2d += it.n; }
+        // ---- kernels
+        int rc;
+        if (op == Op::Unpack) rc = unpack_on_device(D, wn, w_src.data(), w_len.data(), w_dst.data(), w_cap.data(), w_dlen.data(), w_st.data());
+        else rc = pack_on_device(D, ctx->flags, wn, w_src.data(), w_len.data(), w_dst.data(), w_cap.data(), w_dlen.data(), w_sha.data(), w_st.data(), op == Op::Pack, true);
+        if (rc != MFCAS_OK) return rc;
+        // ---- D2H
+        if (op != Op::Hash) {
+            CopyPlan down;
+            for (size_t k = 0; k < wn; k++) {
+                uint64_t i = sh.idx[pos + k];
+                dst_len[i] = w_dlen[k]; status[i] = w_st[k];
+                if (w_st[k] == 0) down.add(dst[i], w_dst[k], w_dlen[k]);
+            }
+            for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, D.stream)); D.d2h += it.n; }
+            CU(cudaStreamSynchronize(D.stream));
+        } else if (status) {
+            for (size_t k = 0; k < wn; k++) status[sh.idx[pos + k]] = 0;
+        }
+        if (sha1 && op != Op::Unpack)
+            for (size_t k = 0; k < wn; k++) memcpy(sha1 + 20 * sh.idx[pos + k], w_sha.data() + 20 * k, 20);
+        pos = end;
+    }
+    return MFCAS_OK;
+}
+
+int run_batch(mfcas_ctx *ctx, Op op, uint64_t n, const void *const *src, const uint64_t *src_len,
+              void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+    if (!ctx) return MFCAS_E_ARG;
+    if (n == 0) return MFCAS_OK;
+    if (!src || !src_len) return MFCAS_E_ARG;
+    if (op != Op::Hash && (!dst || !dst_cap || !dst_len || !status)) return MFCAS_E_ARG;
+    if (op != Op::Unpack && !sha1) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t G = ctx->devs.size();
+    std::vector<Shard> shards(G);
+    for (uint64_t i = 0; i < n; i++) shards[i % G].idx.push_back(i);     // round-robin: blob i -> device i mod G
+    std::vector<int> rcs(G, MFCAS_OK);
+    if (G == 1) {
+        rcs[0] = run_shard(ctx, ctx->devs[0], op, shards[0], src, src_len, dst, dst_cap, dst_len, sha1, status);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++)
+            th.emplace_back([&, g] { rcs[g] = run_shard(ctx, ctx->devs[g], op, shards[g], src, src_len, dst, dst_cap, dst_len, sha1, status); });
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g] != MFCAS_OK) { ctx->err = ctx->devs[g].err; return rcs[g]; }
+    return MFCAS_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *mfcas_version(void) { return MFCAS_VERSION_STR; }
+
+int mfcas_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+mfcas_ctx *mfcas_create(const int *devices, int ndev, uint64_t wave_bytes, uint32_t flags) {
+    int avail = mfcas_device_count();
+    if (avail <= 0) return nullptr;
+    if (ndev <= 0) ndev = avail;
+    mfcas_ctx *ctx = new (std::nothrow) mfcas_ctx();
+    if (!ctx) return nullptr;
+    ctx->flags = flags;
+    if (wave_bytes) ctx->wave_bytes = std::max<uint64_t>(wave_bytes, 1ull << 20);
+    ctx->devs.resize((size_t)ndev);
+    for (int g = 0; g < ndev; g++) {
+        int d = devices ? devices[g] : g;
+        if (d < 0 || d >= avail) { mfcas_destroy(ctx); return nullptr; }
+        ctx->devs[(size_t)g].dev = d;
+        if (device_setup(ctx->devs[(size_t)g]) != MFCAS_OK) {
+            fprintf(stderr, "mfcas_create: %s\n", ctx->devs[(size_t)g].err.c_str());
+            mfcas_destroy(ctx);
+            return nullptr;
+        }
+    }
+    return ctx;
+}
+
+void mfcas_destroy(mfcas_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &D : ctx->devs) device_teardown(D);
+    delete ctx;
+}
+
+const char *mfcas_last_error(mfcas_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void *mfcas_alloc_pinned(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void mfcas_free_pinned(void *p) { if (p) cudaFreeHost(p); }
+
+uint64_t mfcas_pack_bound(uint64_t src_len) { return mf_pack_bound(src_len); }
+
+int mfcas_pack_batch(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len,
+                     void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+    return run_batch(ctx, Op::Pack, n, src, src_len, dst, dst_cap, dst_len, sha1, status);
+}
+
+int mfcas_hash_batch(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len, uint8_t *sha1, int32_t *status) {
+    return run_batch(ctx, Op::Hash, n, src, src_len, nullptr, nullptr, nullptr, sha1, status);
+}
+
+int mfcas_unpack_batch(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len,
+                       void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len, int32_t *status) {
+    return run_batch(ctx, Op::Unpack, n, src, src_len, dst, dst_cap, dst_len, nullptr, status);
+}
+
+int mfcas_unpacked_size(const void *src, uint64_t src_len, uint64_t *size, int *exact) {
+    if (!src || !size) return MFCAS_E_ARG;
+    const uint8_t *p = static_cast<const uint8_t *>(src);
+    uint64_t ip = 0, total = 0;
+    int members = 0;
+    if (exact) *exact = 0;
+    while (ip < src_len) {
+        if (members) { while (ip < src_len && p[ip] == 0) ip++; if (ip >= src_len) break; }
+        uint32_t rl, nc;
+        uint64_t hdr = mf_is_indexed_member(p + ip, src_len - ip, &rl, &nc);
+        if (!hdr) {
+            // foreign stream: ISIZE of the last member is the best hint there is without decoding
+            if (src_len < 18 || p[0] != 0x1f || p[1] != 0x8b) return MFCAS_E_BAD_STREAM;
+            *size = total + mf_le32(p + src_len - 4);
+            return MFCAS_OK;
+        }
+        uint64_t payload = 0;
+        for (uint32_t k = 0; k < nc; k++) payload += mf_le32(p + ip + MF_HDR_FIXED + 8ull * k);
+        if (ip + hdr + payload + MF_TRAILER > src_len) return MFCAS_E_TRUNC;
+        total += rl; members++;
+        ip += hdr + payload + MF_TRAILER;
+    }
+    if (!members) return MFCAS_E_TRUNC;
+    *size = total;
+    if (exact) *exact = 1;
+    return MFCAS_OK;
+}
+
+int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                      void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+    if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return MFCAS_E_ARG;
+    if (n && (!d_src || !src_len || !d_dst || !dst_cap || !dst_len || !sha1 || !status)) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &D = ctx->devs[(size_t)dev_slot];
+    int rc = pack_on_device(D, ctx->flags, n, d_src, src_len, d_dst, dst_cap, dst_len, sha1, status, true, false);
+    if (rc != MFCAS_OK) ctx->err = D.err;
+    return rc;
+}
+
+int mfcas_unpack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                        void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, int32_t *status) {
+    if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return MFCAS_E_ARG;
+    if (n && (!d_src || !src_len || !d_dst || !dst_cap || !dst_len || !status)) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &D = ctx->devs[(size_t)dev_slot];
+    int rc = unpack_on_device(D, n, d_src, src_len, d_dst, dst_cap, dst_len, status);
+    if (rc != MFCAS_OK) ctx->err = D.err;
+    return rc;
+}
+
+void *mfcas_stream(mfcas_ctx *ctx, int dev_slot) {
+    if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return nullptr;
+    return (void *)ctx->devs[(size_t)dev_slot].stream;
+}
+
+void mfcas_counters(mfcas_ctx *ctx, uint64_t *kernel_launches, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
+    uint64_t l = 0, a = 0, b = 0;
+    if (ctx) for (auto &D : ctx->devs) { l += D.launches; a += D.h2d; b += D.d2h; }
+    if (kernel_launches) *kernel_launches = l;
+    if (h2d_bytes) *h2d_bytes = a;
+    if (d2h_bytes) *d2h_bytes = b;
+}
+
+void mfcas_last_kernel_ms(mfcas_ctx *ctx, float out[8]) {
+    for (int i = 0; i < 8; i++) out[i] = 0.f;
+    if (!ctx) return;
+    for (auto &D : ctx->devs) for (int i = 0; i < 8; i++) out[i] = std::max(out[i], D.ms[i]);
+}
+
+}  // extern "C"

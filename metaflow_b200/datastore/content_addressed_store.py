@@ -1,0 +1,201 @@
+"""Content-addressed store with a batched GPU codec.
+
+Same surface and on-disk format as metaflow/datastore/content_addressed_store.py:11-228
+(`ContentAddressedStore(prefix, storage_impl)`, `.TYPE`, `.set_blob_cache`, `save_blobs` :41-120,
+`load_blobs` :122-204, `_pack_v1` :211-216, `_unpack_v1` :218-220, `BlobCache` :223-228):
+key = sha1(blob).hexdigest(), path = <prefix>/<key[:2]>/<key>, sidecar meta
+{"cas_raw": raw, "cas_version": 1}, packed blobs are RFC 1952 files that stock Metaflow reads.
+
+What changes is HOW: the reference hashes and gzips one blob at a time on one CPU core; here the
+iterator is drained in windows, and each window goes through GpuCodec.pack_batch /
+unpack_batch (SHA-1, DEFLATE, CRC-32, INFLATE on the GPUs, sharded round-robin across devices).
+"""
+from collections import namedtuple
+from io import BytesIO
+
+from ..exception import DataException
+from .. import metaflow_config
+
+
+class ContentAddressedStore(object):
+    save_blobs_result = namedtuple("save_blobs_result", "uri key")
+
+    def __init__(self, prefix, storage_impl, codec=None):
+        self._prefix = prefix
+        self._storage_impl = storage_impl
+        self.TYPE = self._storage_impl.TYPE
+        self._blob_cache = None
+        self._codec = codec
+        # bytes of raw blobs gathered before a GPU batch is issued
+        self._window_bytes = int(metaflow_config.GPU_CAS_WAVE_BYTES)
+
+    # -- plumbing ----------------------------------------------------------------------
+    @property
+    def codec(self):
+        if self._codec is None:
+            from ..codec import default_codec  # raises GpuCasUnavailable: no CPU fallback
+
+            self._codec = default_codec()
+        return self._codec
+
+    def set_blob_cache(self, blob_cache):
+        self._blob_cache = blob_cache
+
+    def _path_for(self, key):
+        return self._storage_impl.path_join(self._prefix, key[:2], key)
+
+    def _write(self, items):
+        """items: [(path, bytes-like, meta)] -> storage (zero-copy when the backend can)."""
+        if not items:
+            return
+        if hasattr(self._storage_impl, "save_views"):
+            self._storage_impl.save_views(iter(items))
+        else:
+            self._storage_impl.save_bytes(
+                ((path, (BytesIO(bytes(view)), meta)) for path, view, meta in items),
+                overwrite=True,
+                len_hint=len(items),
+            )
+
+    def _windows(self, blob_iter):
+        batch, size = [], 0
+        for blob in blob_iter:
+            batch.append(blob)
+            size += len(blob[1]) if isinstance(blob, tuple) else len(blob)
+            if size >= self._window_bytes:
+                yield batch
+                batch, size = [], 0
+        if batch:
+            yield batch
+
+    # -- save --------------------------------------------------------------------------
+    def save_blobs(self, blob_iter, raw=False, len_hint=0, is_transfer=False):
+        """Iterator[bytes] -> [save_blobs_result(uri, key)] in input order (uri is None unless raw).
+
+        is_transfer=True: items are (key, bytes, meta) triples coming out of another store's
+        load_blobs(is_transfer=True); they are stored verbatim as raw blobs
+        (content_addressed_store.py:82-96)."""
+        results = []
+        storage = self._storage_impl
+        for window in self._windows(blob_iter):
+            to_write = []
+            if is_transfer:
+                for key, blob_data, _meta in window:
+                    path = self._path_for(key)
+                    results.append(self.save_blobs_result(uri=storage.full_uri(path), key=key))
+                    to_write.append((path, blob_data, {"cas_raw": True, "cas_version": 1}))
+                self._write(to_write)
+                continue
+            if raw:
+                keys, payloads = self.codec.hash_batch(window), window
+            else:
+                keys, payloads = self.codec.pack_batch(window)
+            paths = [self._path_for(k) for k in keys]
+            present = storage.is_file(paths)  # dedup: existing keys are never rewritten (:107)
+            seen = set()
+            meta = {"cas_raw": raw, "cas_version": 1}
+            for key, path, have, payload in zip(keys, paths, present, payloads):
+                results.append(self.save_blobs_result(uri=storage.full_uri(path) if raw else None, key=key))
+                if have or key in seen:
+                    continue
+                seen.add(key)
+                to_write.append((path, payload, meta))
+            self._write(to_write)
+        return results
+
+    # -- load --------------------------------------------------------------------------
+    def load_blobs(self, keys, force_raw=False, is_transfer=False):
+        """Iterable[key] -> iterator of (key, bytes) [(key, bytes, meta) when is_transfer]; order
+        is not guaranteed; one result per requested path (content_addressed_store.py:122-204)."""
+        for item in self._load(keys, force_raw, is_transfer, as_bytes=True):
+            yield item
+
+    def _load(self, keys, force_raw, is_transfer, as_bytes):
+        storage = self._storage_impl
+        pending = []
+        for key in keys:
+            blob = self._blob_cache.load_key(key) if self._blob_cache else None
+            if blob is not None:
+                yield (key, blob, {"cas_raw": False, "cas_version": 1}) if is_transfer else (key, blob)
+            else:
+                pending.append(self._path_for(key))
+        if not pending:
+            return
+        per_blob_unpack = "_unpack_v1" in self.__dict__ or type(self)._unpack_v1 is not ContentAddressedStore._unpack_v1
+        with storage.load_bytes(pending) as loaded:
+            batch, batch_bytes = [], 0
+            for path_key, file_path, meta in loaded:
+                key = storage.path_split(path_key)[-1]
+                with open(file_path, "rb") as f:
+                    if force_raw or (meta and meta.get("cas_raw", False)):
+                        blob = f.read()
+                        if self._blob_cache:
+                            self._blob_cache.store_key(key, blob)
+                        yield (key, blob, meta) if is_transfer else (key, blob)
+                        continue
+                    if meta is None:
+                        unpack_code = self._unpack_backward_compatible  # pre-meta datastores
+                        version = 1
+                    else:
+                        version = meta.get("cas_version", -1)
+                        if version == -1:
+                            raise DataException("Could not extract encoding version for '%s'" % path_key)
+                        unpack_code = getattr(self, "_unpack_v%d" % version, None)
+                        if unpack_code is None:
+                            raise DataException(
+                                "Unknown encoding version %d for '%s' -- the artifact is either corrupt or you "
+                                "need to update Metaflow to the latest version" % (version, path_key)
+                            )
+                    if per_blob_unpack or version != 1:
+                        try:
+                            blob = unpack_code(f)
+                        except Exception as e:
+                            raise DataException("Could not unpack artifact '%s': %s" % (path_key, e))
+                        if self._blob_cache:
+                            self._blob_cache.store_key(key, blob)
+                        yield (key, blob, meta) if is_transfer else (key, blob)
+                        continue
+                    packed = f.read()
+                batch.append((key, path_key, meta, packed))
+                batch_bytes += len(packed)
+                if batch_bytes >= self._window_bytes:
+                    for out in self._flush_unpack(batch, is_transfer, as_bytes):
+                        yield out
+                    batch, batch_bytes = [], 0
+            for out in self._flush_unpack(batch, is_transfer, as_bytes):
+                yield out
+
+    def _flush_unpack(self, batch, is_transfer, as_bytes):
+        if not batch:
+            return
+        decoded = self.codec.unpack_batch([b[3] for b in batch], as_bytes=as_bytes or bool(self._blob_cache))
+        for (key, path_key, meta, _), blob in zip(batch, decoded):
+            if isinstance(blob, Exception):
+                raise DataException("Could not unpack artifact '%s': %s" % (path_key, blob))
+            if self._blob_cache:
+                self._blob_cache.store_key(key, blob)
+            yield (key, blob, meta) if is_transfer else (key, blob)
+
+    # -- the versioned codec hooks of the reference, kept as single-blob entry points ---
+    def _unpack_backward_compatible(self, blob):
+        return self._unpack_v1(blob)
+
+    def _pack_v1(self, blob):
+        """bytes -> BytesIO of the RFC 1952 file (one-blob batch through the GPU codec)."""
+        _, packed = self.codec.pack_batch([blob])
+        return BytesIO(bytes(packed[0]))
+
+    def _unpack_v1(self, blob):
+        """file object -> decoded bytes (one-blob batch through the GPU codec)."""
+        out = self.codec.unpack_batch([blob.read()])[0]
+        if isinstance(out, Exception):
+            raise out
+        return out
+
+
+class BlobCache(object):
+    def load_key(self, key):
+        pass
+
+    def store_key(self, key, blob):
+        pass

@@ -1,0 +1,35 @@
+"""The handful of configuration knobs the datastore path reads.
+
+Same precedence idea as metaflow/metaflow_config_funcs.py:84-140 (`from_conf`): the
+environment variable METAFLOW_<NAME> wins over the default.  (Profile JSON files are
+part of the reference's config subsystem, which is out of scope here.)
+"""
+import json
+import os
+
+
+def from_conf(name, default=None, validate_fn=None):
+    raw = os.environ.get("METAFLOW_%s" % name)
+    if raw is None:
+        return default
+    if default is not None and not isinstance(default, str):
+        try:
+            raw = type(default)(json.loads(raw)) if not isinstance(default, bool) else raw.lower() in ("1", "true", "yes")
+        except (ValueError, TypeError):
+            raise ValueError("METAFLOW_%s has an invalid value %r" % (name, raw))
+    if validate_fn:
+        validate_fn(name, raw)
+    return raw
+
+
+# metaflow_config.py:29,39,98,604,525
+DATASTORE_LOCAL_DIR = ".metaflow"
+DEFAULT_DATASTORE = from_conf("DEFAULT_DATASTORE", "local")
+DATASTORE_SYSROOT_LOCAL = from_conf("DATASTORE_SYSROOT_LOCAL")
+MAX_ATTEMPTS = from_conf("MAX_ATTEMPTS", 6)
+PROFILE_FROM_START = from_conf("PROFILE_FROM_START", False)
+
+# New knobs for the GPU path (SURVEY.md section 5 proposal).
+GPU_CAS_DEVICES = from_conf("GPU_CAS_DEVICES", "")            # "" = all visible; else "0,1,.."
+GPU_CAS_WAVE_BYTES = from_conf("GPU_CAS_WAVE_BYTES", 1 << 30)  # bytes of blobs packed per GPU wave
+GPU_CAS_LZ = from_conf("GPU_CAS_LZ", 1)                        # 0 = Huffman-only encoder

@@ -1,0 +1,96 @@
+"""CPU checks of the codec's host/device-shared code (mf_core.h, mf_inflate_core.h) compiled with
+g++: Huffman builder, block-header writer, bit packer, GF(2) CRC arithmetic, member layout and the
+serial inflater, validated against zlib / gzip and the C oracle."""
+import gzip
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import model_lib
+from oracle import c_oracle
+
+
+def _cases():
+    rng = np.random.default_rng(0)
+    return {
+        "empty": b"",
+        "one": b"a",
+        "abc": b"abc" * 3,
+        "zeros": bytes(200000),
+        "normal": rng.standard_normal(70000, dtype=np.float32).tobytes(),
+        "uniform": rng.random(30000, dtype=np.float32).tobytes(),
+        "lowent": rng.integers(0, 16, 60000).astype(np.float32).tobytes(),
+        "text": b"The quick brown fox jumps over the lazy dog. " * 2000,
+        "random": rng.bytes(100001),
+        "ramp": bytes(range(256)) * 300,
+        "seg_edge": rng.bytes(1024) + b"x" * 1024 + rng.bytes(7),
+        "skew": bytes([0] * 60000 + list(range(256))),
+        "chunk_minus1": rng.bytes(32767),
+        "chunk_exact": rng.integers(0, 4, 32768).astype(np.uint8).tobytes(),
+        "chunk_plus1": rng.integers(0, 4, 32769).astype(np.uint8).tobytes(),
+    }
+
+
+@pytest.mark.parametrize("lz", [0, 1])
+def test_model_stream_is_valid_gzip(lz):
+    for name, blob in _cases().items():
+        z = model_lib.pack(blob, lz)
+        assert len(z) <= model_lib.lib().model_pack_bound(len(blob)), name
+        assert gzip.decompress(z) == blob, name            # CPython gzip = what the reference's reader runs
+        e, out = c_oracle.gunzip(z, len(blob))             # independent RFC 1951/1952 restatement
+        assert e == 0 and out == blob, (name, e)
+        e, out = model_lib.gunzip(z, len(blob))            # the product's serial inflater (foreign path)
+        assert e == 0 and out == blob, (name, e)
+        e, out = model_lib.unpack_indexed(z, len(blob))    # segment-parallel decoding order
+        assert e == 0 and out == blob, (name, e)
+
+
+def test_model_ratio_not_worse_than_zlib_level1_on_float_noise():
+    rng = np.random.default_rng(3)
+    for blob in (rng.standard_normal(200000, dtype=np.float32).tobytes(), rng.random(200000, dtype=np.float32).tobytes()):
+        ours = len(model_lib.pack(blob, 1))
+        assert ours <= len(gzip.compress(blob, 1)) * 1.005
+
+
+def test_serial_inflater_on_zlib_streams():
+    for name, blob in _cases().items():
+        for level in (0, 1, 3, 9):
+            z = gzip.compress(blob, level)
+            e, out = model_lib.gunzip(z + z + b"\0" * 5, 2 * len(blob))
+            assert e == 0 and out == blob + blob, (name, level, e)
+    co = zlib.compressobj(9, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)   # fixed-Huffman blocks
+    data = b"abcabcabc" * 500
+    z = co.compress(data) + co.flush()
+    e, out = model_lib.gunzip(z, len(data))
+    assert e == 0 and out == data
+
+
+def test_multi_member_boundary():
+    rng = np.random.default_rng(5)
+    n = 768 * 32768                       # MF_MEMBER_RAW
+    for size in (n - 1, n, n + 1):
+        blob = rng.integers(0, 8, size).astype(np.uint8).tobytes()
+        z = model_lib.pack(blob, 1)
+        assert gzip.decompress(z) == blob
+        e, out = model_lib.unpack_indexed(z, size)
+        assert e == 0 and out == blob
+
+
+def test_corruption_is_detected():
+    blob = np.random.default_rng(1).standard_normal(50000, dtype=np.float32).tobytes()
+    z = bytearray(model_lib.pack(blob, 1))
+    z[len(z) // 2] ^= 0x10
+    e1, _ = model_lib.unpack_indexed(bytes(z), len(blob))
+    e2, _ = model_lib.gunzip(bytes(z), len(blob))
+    assert e1 != 0 and e2 != 0
+    with pytest.raises(Exception):
+        gzip.decompress(bytes(z))
+    z = bytearray(model_lib.pack(blob, 1))
+    z[-6] ^= 1                             # CRC field
+    assert model_lib.unpack_indexed(bytes(z), len(blob))[0] == 4
+    assert model_lib.gunzip(bytes(z), len(blob))[0] == 4
+    for cut in (5, 40, len(z) // 2, len(z) - 3):
+        assert model_lib.gunzip(bytes(z[:cut]), len(blob))[0] != 0
+    assert model_lib.gunzip(os.urandom(64), 1000)[0] != 0
