@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- artifact GB/s through save+load of the content-addressed store (BASELINE.json metric).
+
+Workload (BASELINE.json configs[1]): a 4096-way foreach whose tasks each persist one 16 MiB fp32
+N(0,1) numpy array (pickle protocol 4 -> 16,777,379-byte blob).  One STEP = one wave of
+`--blobs-per-step` such blobs per GPU going through the whole hot path:
+    save: SHA-1 key + DEFLATE + CRC-32 -> RFC 1952 file      (mfcas_pack_*)
+    load: INFLATE + CRC-32/ISIZE verification -> blob bytes  (mfcas_unpack_*)
+With the defaults (512 blobs/step, 8 steps) the job is exactly the 4096 blobs.  Round-robin sharding:
+blob i of the global batch belongs to rank i mod N (weak scaling: per-GPU wave size is fixed).
+
+  value : round-trip GB/s with inputs/outputs resident in HBM (mfcas_pack_device / _unpack_device),
+          CUDA events on the library stream, max over ranks.
+  e2e   : the same metric through the host-pointer C ABI (mfcas_pack_batch / _unpack_batch) from
+          page-locked host buffers, H2D and D2H inside the timed region.
+  --impl reference : the reference's CPU path (hashlib.sha1 + gzip level 3 + gunzip + local CAS
+          files, restated in oracle/ref_path.py) on all host cores, bounded sample per step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import pickle
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+ARRAY_ELEMS = 4194304            # 16 MiB of float32
+METRIC = "artifact_roundtrip_GBps"
+UNIT = "GB/s"
+
+
+def pickle_frame(n_elems):
+    """(prefix, suffix, nbytes): pickle.dumps(float32[n], protocol=4) == prefix + raw + suffix."""
+    probe = np.full(n_elems, 1.5, dtype=np.float32)
+    p = pickle.dumps(probe, protocol=4)
+    raw = probe.tobytes()
+    off = p.index(raw[:64])
+    assert p[off:off + len(raw)] == raw
+    return p[:off], p[off + len(raw):], len(raw)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler(object):
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True); self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- reference (CPU) arm
+def _cpu_worker(args):
+    """One process = one reference task: generate, save through the restated path, load back."""
+    worker, n_blobs, root, seed0 = args
+    from oracle import ref_path
+    blobs = [pickle.dumps(np.random.default_rng(seed0 + worker * 1000 + j).standard_normal(ARRAY_ELEMS, dtype=np.float32), protocol=4)
+             for j in range(n_blobs)]
+    t0 = time.perf_counter()
+    res = ref_path.save_blobs(root, "BenchFlow/data", blobs)
+    t1 = time.perf_counter()
+    back = ref_path.load_blobs(root, "BenchFlow/data", [k for _, k in res])
+    t2 = time.perf_counter()
+    ok = all(b == o for b, (_, o) in zip(blobs, back))
+    return sum(map(len, blobs)), t1 - t0, t2 - t1, ok
+
+
+def cpu_reference_pass(n_procs, blobs_per_proc, seed0):
+    """Process-per-task parallelism of the reference (runtime.py:1517-1540, --max-workers) on a tmpfs
+    datastore.  Returns (bytes, t_save, t_load): slowest worker's in-call times."""
+    import multiprocessing as mp
+    import shutil
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = tempfile.mkdtemp(prefix="mfcas_ref_", dir=base)
+    try:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(n_procs) as pool:
+            out = pool.map(_cpu_worker, [(w, blobs_per_proc, root, seed0) for w in range(n_procs)])
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    assert all(o[3] for o in out), "reference arm round-trip mismatch"
+    return sum(o[0] for o in out), max(o[1] for o in out), max(o[2] for o in out)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per = max(1, args.ref_blobs_per_proc)
+    for i in range(args.warmup):
+        cpu_reference_pass(cores, 1 if i else 1, 7_000_000 + i)
+    tot_b = tot_s = tot_l = 0.0
+    for s in range(args.steps):
+        b, ts, tl = cpu_reference_pass(cores, per, 1_000_000 * (s + 1))
+        tot_b += b; tot_s += ts; tot_l += tl
+    value = tot_b / (tot_s + tot_l) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (tot_s + tot_l) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "impl": "reference",
+        "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts, save_blobs+load_blobs", "sample": "%d blobs/step (%d procs x %d)" % (cores * per, cores, per),
+                   "datastore": "local on tmpfs"},
+        "save_GBps": tot_b / tot_s / 1e9, "load_GBps": tot_b / tot_l / 1e9,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d x 16 MiB blobs per step through oracle/ref_path.py (hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files), process per task" % (cores * per)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    from metaflow_b200 import capi
+    lib = capi.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    devs = (ctypes.c_int * 1)(local_rank)
+    ctx = lib.mfcas_create(devs, 1, args.wave_gib << 30, 0)
+    if not ctx:
+        raise SystemExit("mfcas_create failed: no CUDA device -- the hot path has no CPU fallback")
+    ctx = ctypes.c_void_p(ctx)
+    prefix, suffix, nbytes = pickle_frame(ARRAY_ELEMS)
+    blob_len = len(prefix) + nbytes + len(suffix)
+    B = args.blobs_per_step
+    stride = (blob_len + 255) // 256 * 256 + 256
+    cap = lib.mfcas_pack_bound(blob_len)
+    cstride = (cap + 255) // 256 * 256 + 256
+
+    d_in = torch.empty(B * stride, dtype=torch.uint8, device=dev)
+    d_packed = torch.empty(B * cstride, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(B * stride, dtype=torch.uint8, device=dev)
+    d_rand = torch.empty(ARRAY_ELEMS, dtype=torch.float32, device=dev)
+    t_prefix = torch.frombuffer(bytearray(prefix), dtype=torch.uint8).to(dev)
+    t_suffix = torch.frombuffer(bytearray(suffix), dtype=torch.uint8).to(dev)
+    gen = torch.Generator(device=dev)
+
+    def generate(step):
+        # blob i of this rank's wave is global blob (step*B + i)*world + rank  (round-robin i mod N)
+        for i in range(B):
+            gen.manual_seed(((step * B + i) * world + rank) * 2654435761 % (1 << 62))
+            d_rand.normal_(generator=gen)
+            o = i * stride
+            d_in[o:o + len(prefix)] = t_prefix
+            d_in[o + len(prefix):o + len(prefix) + nbytes] = d_rand.view(torch.uint8)
+            d_in[o + len(prefix) + nbytes:o + blob_len] = t_suffix
+        torch.cuda.synchronize()
+
+    u64, vp = ctypes.c_uint64, ctypes.c_void_p
+    n = B
+    src = (vp * n)(*[d_in.data_ptr() + i * stride for i in range(n)])
+    slen = (u64 * n)(*([blob_len] * n))
+    pk = (vp * n)(*[d_packed.data_ptr() + i * cstride for i in range(n)])
+    pcap = (u64 * n)(*([cap] * n))
+    plen = (u64 * n)()
+    out = (vp * n)(*[d_out.data_ptr() + i * stride for i in range(n)])
+    ocap = (u64 * n)(*([blob_len] * n))
+    olen = (u64 * n)()
+    st = (ctypes.c_int32 * n)()
+    sha = ctypes.create_string_buffer(20 * n)
+    stream = torch.cuda.ExternalStream(lib.mfcas_stream(ctx, 0), device=dev)
+
+    def check(rc, what):
+        if rc != 0 or any(st):
+            raise SystemExit("%s failed rc=%d status=%s: %s" % (what, rc, [s for s in st if s][:4], lib.mfcas_last_error(ctx)))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record(stream)
+        check(lib.mfcas_pack_device(ctx, 0, n, src, slen, pk, pcap, plen, sha, st), "pack_device")
+        e1.record(stream)
+        check(lib.mfcas_unpack_device(ctx, 0, n, pk, plen, out, ocap, olen, st), "unpack_device")
+        e2.record(stream)
+        torch.cuda.synchronize()
+        ms = (ctypes.c_float * 8)()
+        lib.mfcas_last_kernel_ms(ctx, ms)
+        return e0.elapsed_time(e1), e1.elapsed_time(e2), list(ms)
+
+    def verify(sample):
+        import gzip
+        import hashlib
+        for i in sample:
+            blob = d_in[i * stride:i * stride + blob_len].cpu().numpy().tobytes()
+            assert sha.raw[20 * i:20 * i + 20] == hashlib.sha1(blob).digest(), "sha1 mismatch blob %d" % i
+            z = d_packed[i * cstride:i * cstride + plen[i]].cpu().numpy().tobytes()
+            assert gzip.decompress(z) == blob, "reference reader cannot decode blob %d" % i
+            assert d_out[i * stride:i * stride + blob_len].cpu().numpy().tobytes() == blob, "decoded bytes differ blob %d" % i
+            arr = pickle.loads(blob)
+            assert arr.dtype == np.float32 and arr.shape == (ARRAY_ELEMS,)
+
+    # ---- warm-up (untimed) + parity gate
+    for w in range(args.warmup):
+        generate(10_000 + w)
+        step_device()
+    verify(sorted(set([0, n // 2, n - 1])))
+
+    # ---- HBM-resident timed steps
+    counters0 = [u64(0), u64(0), u64(0)]
+    lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in counters0])
+    sampler = ClockSampler(local_rank)
+    t_save = t_load = 0.0
+    kms = [0.0] * 8
+    packed_bytes = 0
+    barrier()
+    sampler.start()
+    for s in range(args.steps):
+        generate(s)
+        a, b, ms = step_device()
+        t_save += a; t_load += b
+        kms = [x + y for x, y in zip(kms, ms)]
+        packed_bytes += sum(plen)
+    barrier()
+    clocks = sampler.stop()
+    counters1 = [u64(0), u64(0), u64(0)]
+    lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in counters1])
+    launches = counters1[0].value - counters0[0].value
+    verify([1])
+    raw_bytes = args.steps * n * blob_len
+
+    # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies timed)
+    h_in_p = lib.mfcas_alloc_pinned(B * stride); h_pk_p = lib.mfcas_alloc_pinned(B * cstride); h_out_p = lib.mfcas_alloc_pinned(B * stride)
+    assert h_in_p and h_pk_p and h_out_p, "pinned allocation failed"
+    h_in = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_in_p))
+    h_out = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_out_p))
+    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (B * cstride)).from_address(h_pk_p))
+    hsrc = (vp * n)(*[h_in_p + i * stride for i in range(n)])
+    hpk = (vp * n)(*[h_pk_p + i * cstride for i in range(n)])
+    hout = (vp * n)(*[h_out_p + i * stride for i in range(n)])
+    t_in = torch.from_numpy(h_in)
+    e2e_save = e2e_load = 0.0
+    e2e_steps = args.steps
+    h2d = d2h = 0
+
+    def step_host():
+        t0 = time.perf_counter()
+        check(lib.mfcas_pack_batch(ctx, n, hsrc, slen, hpk, pcap, plen, sha, st), "pack_batch")
+        t1 = time.perf_counter()
+        check(lib.mfcas_unpack_batch(ctx, n, hpk, plen, hout, ocap, olen, st), "unpack_batch")
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    generate(20_000); t_in.copy_(d_in.cpu()); step_host()       # warm-up (arena allocation)
+    import hashlib
+    blob0 = h_in[:blob_len].tobytes()
+    assert sha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
+    barrier()
+    for s in range(e2e_steps):
+        generate(30_000 + s)
+        t_in.copy_(d_in.cpu())
+        barrier()
+        a, b = step_host()
+        e2e_save += a; e2e_load += b
+        pb = sum(plen)
+        h2d += n * blob_len + pb; d2h += pb + n * blob_len
+    assert h_out[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes() == h_in[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes()
+
+    # ---- reduce over ranks (max time), aggregate
+    times = torch.tensor([t_save, t_load, e2e_save * 1e3, e2e_load * 1e3] + kms, dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_save, t_load, e2e_save_ms, e2e_load_ms = (float(x) for x in times[:4])
+    kms = [float(x) for x in times[4:]]
+    total_raw = raw_bytes * world
+    value = total_raw / ((t_save + t_load) * 1e-3) / 1e9
+    e2e_value = total_raw / ((e2e_save_ms + e2e_load_ms) * 1e-3) / 1e9
+
+    if rank == 0:
+        peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as f:
+                peak, peak_src = json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        names = ["sha1", "deflate", "gather", "inflate", "verify+foreign"]
+        dominant = max(range(4), key=lambda i: kms[i])
+        ratio = packed_bytes / raw_bytes
+        # algorithmic bytes of the dominant kernel per launch (save N+C+20, load C+N)
+        alg = {0: n * blob_len + 20 * n, 1: n * blob_len * (1 + ratio), 2: 2 * n * blob_len * ratio, 3: n * blob_len * (1 + ratio)}[dominant]
+        dom_ms = kms[dominant] / args.steps
+        achieved = alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(REPO, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(names[dominant])
+        cpu = None
+        if not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            per = max(1, args.ref_blobs_per_proc)
+            cpu_reference_pass(cores, 1, 99)
+            b, ts, tl = cpu_reference_pass(cores, per, 5_000_000)
+            cpu = {"value": b / (ts + tl) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d x 16 MiB blobs (%d procs x %d) through oracle/ref_path.py: hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files" % (cores * per, cores, per),
+                   "save_GBps": b / ts / 1e9, "load_GBps": b / tl / 1e9}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": (t_save + t_load) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts (pickle blob %d B), save+load" % blob_len,
+                       "blobs_per_step_per_gpu": n, "blobs_total": n * args.steps * world, "sharding": "round-robin blob i -> rank i mod N, no collective",
+                       "l2": "inputs %.1f GB per step >> 126 MB L2 (no flush needed)" % (n * blob_len / 1e9), "packed_ratio": ratio},
+            "save_GBps": total_raw / (t_save * 1e-3) / 1e9, "load_GBps": total_raw / (t_load * 1e-3) / 1e9,
+            "kernel_ms_per_step": {nm: k / args.steps for nm, k in zip(names, kms)},
+            "roofline": {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+                    "save_GBps": total_raw / (e2e_save_ms * 1e-3) / 1e9, "load_GBps": total_raw / (e2e_load_ms * 1e-3) / 1e9,
+                    "api": "mfcas_pack_batch + mfcas_unpack_batch on page-locked host buffers"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    lib.mfcas_free_pinned(h_in_p); lib.mfcas_free_pinned(h_pk_p); lib.mfcas_free_pinned(h_out_p)
+    lib.mfcas_destroy(ctx)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--blobs-per-step", type=int, default=512)
+    ap.add_argument("--wave-gib", type=int, default=24, help="device arena per wave for the host-pointer API")
+    ap.add_argument("--ref-blobs-per-proc", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,250 @@
+"""GPU parity tests proper (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(GpuCodec -> libmfcas.so), against the CPU oracle on the same inputs.  Bit-exact everywhere:
+keys == hashlib.sha1, decoded bytes == input, our files decode with CPython gzip (what the
+reference's _unpack_v1 runs) and with the independent C oracle, reference-written files decode
+on the GPU."""
+import base64
+import ctypes
+import gzip
+import hashlib
+import json
+import os
+import pickle
+import zlib
+
+import numpy as np
+import pytest
+
+import golden_inputs
+from oracle import c_oracle, ref_path
+
+pytestmark = pytest.mark.gpu
+
+
+def _roundtrip(codec, blobs):
+    keys, packed = codec.pack_batch(blobs)
+    packed = [bytes(p) for p in packed]
+    for i, (b, k, z) in enumerate(zip(blobs, keys, packed)):
+        b = bytes(b)
+        assert k == hashlib.sha1(b).hexdigest(), i
+        assert z[:4] == b"\x1f\x8b\x08\x04", i
+        assert gzip.decompress(z) == b, i
+        e, out = c_oracle.gunzip(z, len(b))
+        assert e == 0 and out == b, (i, e)
+    back = codec.unpack_batch(packed)
+    for i, (b, o) in enumerate(zip(blobs, back)):
+        assert not isinstance(o, Exception), (i, o)
+        assert o == bytes(b), i
+    return keys, packed
+
+
+def test_golden_raw_blobs(gpu_codec, golden):
+    blobs = golden_inputs.raw_blobs()
+    names = list(blobs)
+    keys, _ = _roundtrip(gpu_codec, [blobs[n] for n in names])
+    assert keys == [golden["raw_blobs"][n]["key"] for n in names]
+    assert gpu_codec.hash_batch([blobs[n] for n in names]) == keys
+
+
+def test_golden_artifacts_and_reference_written_files(gpu_codec, golden):
+    objs = golden_inputs.artifact_objects()
+    names = list(objs)
+    pickles = [pickle.dumps(objs[n], protocol=4) for n in names]
+    keys, _ = _roundtrip(gpu_codec, pickles)
+    assert keys == [golden["data_json"]["objects"][n] for n in names]
+    # files the REAL reference wrote (zlib level 3, single stream) decode on the GPU
+    ref_files = [base64.b64decode(golden["artifacts"][n]["gz_b64"]) for n in names]
+    ref_files += [base64.b64decode(g["gz_b64"]) for g in golden["raw_blobs"].values()]
+    want = pickles + list(golden_inputs.raw_blobs().values())
+    got = gpu_codec.unpack_batch(ref_files)
+    for i, (w, g) in enumerate(zip(want, got)):
+        assert not isinstance(g, Exception), (i, g)
+        assert g == w, i
+
+
+def test_edge_sizes_ragged_batch(gpu_codec):
+    rng = np.random.default_rng(7)
+    sizes = [0, 1, 2, 3, 4, 5, 15, 16, 17, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1023, 1024, 1025, 2047, 2048, 2049,
+             4095, 32767, 32768, 32769, 65535, 65536, 65537, 100000, 0, 1]
+    blobs = []
+    for i, n in enumerate(sizes):
+        kind = i % 4
+        if kind == 0:
+            blobs.append(rng.bytes(n))
+        elif kind == 1:
+            blobs.append(bytes(n))
+        elif kind == 2:
+            blobs.append((b"metaflow foreach join artifact " * (n // 31 + 1))[:n])
+        else:
+            blobs.append(rng.integers(0, 5, n).astype(np.uint8).tobytes())
+    _roundtrip(gpu_codec, blobs)
+
+
+def test_distributions_and_ratio(gpu_codec):
+    rng = np.random.default_rng(11)
+    n = 1 << 18
+    data = {
+        "normal": rng.standard_normal(n, dtype=np.float32).tobytes(),
+        "uniform": rng.random(n, dtype=np.float32).tobytes(),
+        "lowent": rng.integers(0, 16, n).astype(np.float32).tobytes(),
+        "zeros": bytes(4 * n),
+        "text": (open(gzip.__file__, "rb").read() * 40)[: 4 * n],
+        "int64": np.arange(n // 2, dtype=np.int64).tobytes(),
+    }
+    _, packed = _roundtrip(gpu_codec, list(data.values()))
+    ratios = {k: len(z) / len(b) for (k, b), z in zip(data.items(), packed)}
+    print("ratios", {k: round(v, 4) for k, v in ratios.items()})
+    for k in ("normal", "uniform"):
+        assert ratios[k] <= len(gzip.compress(data[k], 1)) / len(data[k]) * 1.005, k   # >= zlib level 1 on float noise
+    assert ratios["zeros"] < 0.02 and ratios["lowent"] < 0.32 and ratios["text"] < 0.6
+
+
+def test_member_boundaries(gpu_codec):
+    rng = np.random.default_rng(3)
+    n = 768 * 32768
+    blobs = [rng.integers(0, 8, size).astype(np.uint8).tobytes() for size in (n - 1, n, n + 1, 2 * n + 12345)]
+    _roundtrip(gpu_codec, blobs)
+
+
+def test_foreign_streams(gpu_codec):
+    rng = np.random.default_rng(5)
+    payloads = [b"", b"x", rng.bytes(70000), b"hello world " * 5000, rng.standard_normal(80000, dtype=np.float32).tobytes(), bytes(300000)]
+    files, want = [], []
+    for p in payloads:
+        for level in (0, 1, 3, 9):
+            files.append(gzip.compress(p, level)); want.append(p)
+    files.append(gzip.compress(payloads[2], 3) + gzip.compress(payloads[3], 9) + b"\0" * 9); want.append(payloads[2] + payloads[3])
+    co = zlib.compressobj(9, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)
+    files.append(co.compress(payloads[3]) + co.flush()); want.append(payloads[3])
+    import io
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="named.bin", fileobj=buf, mode="wb", compresslevel=3) as f:   # FNAME header field
+        f.write(payloads[4])
+    files.append(buf.getvalue()); want.append(payloads[4])
+    files.append(c_oracle.gzip_stored(payloads[2], mtime=3)); want.append(payloads[2])
+    got = gpu_codec.unpack_batch(files)
+    for i, (w, g) in enumerate(zip(want, got)):
+        assert not isinstance(g, Exception), (i, g)
+        assert g == w, i
+
+
+def test_corruption_and_error_text(gpu_codec, tmp_path):
+    from metaflow_b200 import capi
+    blob = np.random.default_rng(1).standard_normal(60000, dtype=np.float32).tobytes()
+    _, packed = gpu_codec.pack_batch([blob])
+    good = bytes(packed[0])
+    crc_flip = bytearray(good); crc_flip[-6] ^= 1
+    isize_flip = bytearray(good); isize_flip[-1] ^= 1
+    payload_flip = bytearray(good); payload_flip[len(good) // 2] ^= 0x20
+    ref = bytearray(gzip.compress(blob, 3)); ref[-6] ^= 1
+    ref_trunc = gzip.compress(blob, 3)[:-20]
+    cases = [bytes(crc_flip), bytes(isize_flip), bytes(payload_flip), bytes(ref), ref_trunc, b"definitely not gzip data", good[: len(good) // 2], good]
+    out = gpu_codec.unpack_batch(cases)
+    assert out[0].code == capi.E_BAD_CRC and "CRC check failed" in str(out[0])
+    assert isinstance(out[1], Exception) and isinstance(out[2], Exception)
+    assert out[3].code == capi.E_BAD_CRC
+    assert isinstance(out[4], Exception) and isinstance(out[5], Exception) and isinstance(out[6], Exception)
+    assert out[7] == blob                                  # a good blob in the same batch is unaffected
+    # through the datastore class the failure surfaces as the reference's DataException text
+    from metaflow_b200 import FlowDataStore, LocalStorage
+    from metaflow_b200.exception import DataException
+    fds = FlowDataStore("C", storage_impl=LocalStorage, ds_root=str(tmp_path), codec=gpu_codec)
+    key = fds.ca_store.save_blobs(iter([blob]))[0].key
+    p = tmp_path / "C" / "data" / key[:2] / key
+    p.write_bytes(bytes(crc_flip))
+    with pytest.raises(DataException) as e:
+        list(fds.ca_store.load_blobs([key]))
+    assert "Could not unpack artifact 'C/data/%s/%s'" % (key[:2], key) in str(e.value) and "CRC check failed" in str(e.value)
+
+
+def test_datastore_end_to_end_on_gpu(gpu_codec, tmp_path, golden):
+    from metaflow_b200 import FlowDataStore, LocalStorage
+    objs = golden_inputs.artifact_objects()
+    fds = FlowDataStore("GoldenFlow", storage_impl=LocalStorage, ds_root=str(tmp_path), codec=gpu_codec)
+    w = fds.get_task_datastore("1", "start", "7", attempt=0, mode="w")
+    w.init_task(); w.save_artifacts(iter(objs.items()), len_hint=len(objs)); w.done()
+    dj = json.loads((tmp_path / "GoldenFlow" / "1" / "start" / "7" / "0.data.json").read_text())
+    assert dj["objects"] == golden["data_json"]["objects"] and dj["info"] == golden["data_json"]["info"]
+    for name, key in dj["objects"].items():                # every stored file is plain gzip to the reference
+        z = (tmp_path / "GoldenFlow" / "data" / key[:2] / key).read_bytes()
+        assert ref_path.unpack_v1(z) == pickle.dumps(objs[name], protocol=4)
+        assert json.loads((tmp_path / "GoldenFlow" / "data" / key[:2] / (key + "_meta")).read_text()) == {"cas_raw": False, "cas_version": 1}
+    back = dict(fds.get_task_datastore("1", "start", "7").load_artifacts(list(objs)))
+    for n, o in objs.items():
+        assert (np.array_equal(o, back[n]) and o.dtype == back[n].dtype) if isinstance(o, np.ndarray) else o == back[n], n
+    # files written by the reference's code path (restated: gzip level 3) load through the GPU
+    ref_root = tmp_path / "ref"
+    objects, info = ref_path.save_artifacts(str(ref_root), "GoldenFlow", objs.items())
+    assert objects == dj["objects"] and info == dj["info"]
+    fds2 = FlowDataStore("GoldenFlow", storage_impl=LocalStorage, ds_root=str(ref_root), codec=gpu_codec)
+    got = dict(fds2.ca_store.load_blobs(list(set(objects.values()))))
+    for name, key in objects.items():
+        assert got[key] == pickle.dumps(objs[name], protocol=4)
+
+
+def test_no_lz_flag_and_wave_splitting():
+    from metaflow_b200.codec import GpuCodec
+    rng = np.random.default_rng(2)
+    blobs = [rng.integers(0, 3, 300000).astype(np.uint8).tobytes() for _ in range(9)] + [b"", b"tiny"]
+    c = GpuCodec(wave_bytes=1 << 20, lz=False)             # 1 MiB waves -> the batch is cut into several
+    try:
+        _roundtrip(c, blobs)
+        assert c.counters()["kernel_launches"] >= 3 * 4
+    finally:
+        c.close()
+
+
+def test_baseline_size_properties(gpu_codec):
+    """BASELINE.json config-2 blob size (16 MiB fp32 -> 16,777,379-byte pickle), size-independent
+    properties: encode -> decode round trip, keys == hashlib, checksum of checksums."""
+    n = 12
+    arrays = [np.random.default_rng(100 + i).standard_normal(4194304, dtype=np.float32) for i in range(n)]
+    blobs = [pickle.dumps(a, protocol=4) for a in arrays]
+    assert len(blobs[0]) == 16777379
+    keys, packed = gpu_codec.pack_batch(blobs)
+    packed = [bytes(p) for p in packed]
+    assert keys == [hashlib.sha1(b).hexdigest() for b in blobs]
+    back = gpu_codec.unpack_batch(packed)
+    agg = hashlib.sha1()
+    for b, o in zip(blobs, back):
+        assert o == b
+        agg.update(hashlib.sha1(o).digest())
+    want = hashlib.sha1()
+    for k in keys:
+        want.update(bytes.fromhex(k))
+    assert agg.digest() == want.digest()
+    assert gzip.decompress(packed[3]) == blobs[3]           # the reference's reader on a full-size blob
+    ratio = sum(map(len, packed)) / sum(map(len, blobs))
+    print("16 MiB N(0,1) ratio", ratio)
+    assert ratio < 0.935
+
+
+def test_device_resident_api(gpu_codec):
+    import torch
+    from metaflow_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(9)
+    blobs = [rng.standard_normal(50000, dtype=np.float32).tobytes(), b"", rng.bytes(33333)]
+    d_src = [torch.frombuffer(bytearray(b) + bytearray(16), dtype=torch.uint8).cuda() for b in blobs]
+    caps = [lib.mfcas_pack_bound(len(b)) for b in blobs]
+    d_dst = [torch.zeros(c + 16, dtype=torch.uint8, device="cuda") for c in caps]
+    torch.cuda.synchronize()
+    n = len(blobs)
+    src = (ctypes.c_void_p * n)(*[t.data_ptr() for t in d_src]); dst = (ctypes.c_void_p * n)(*[t.data_ptr() for t in d_dst])
+    slen = (ctypes.c_uint64 * n)(*[len(b) for b in blobs]); cap = (ctypes.c_uint64 * n)(*caps)
+    dlen = (ctypes.c_uint64 * n)(); st = (ctypes.c_int32 * n)(); sha = ctypes.create_string_buffer(20 * n)
+    assert lib.mfcas_pack_device(gpu_codec._ctx, 0, n, src, slen, dst, cap, dlen, sha, st) == 0
+    assert list(st) == [0] * n
+    for i, b in enumerate(blobs):
+        assert sha.raw[20 * i:20 * i + 20] == hashlib.sha1(b).digest()
+        z = d_dst[i][: dlen[i]].cpu().numpy().tobytes()
+        assert gzip.decompress(z) == b
+    d_out = [torch.zeros(len(b) + 16, dtype=torch.uint8, device="cuda") for b in blobs]
+    torch.cuda.synchronize()
+    out = (ctypes.c_void_p * n)(*[t.data_ptr() for t in d_out]); ocap = (ctypes.c_uint64 * n)(*[len(b) for b in blobs])
+    olen = (ctypes.c_uint64 * n)(); st2 = (ctypes.c_int32 * n)()
+    assert lib.mfcas_unpack_device(gpu_codec._ctx, 0, n, dst, dlen, out, ocap, olen, st2) == 0
+    assert list(st2) == [0] * n
+    for i, b in enumerate(blobs):
+        assert olen[i] == len(b) and d_out[i][: len(b)].cpu().numpy().tobytes() == b
+    assert lib.mfcas_stream(gpu_codec._ctx, 0)
