@@ -19,9 +19,13 @@ struct MfHashDesc {
 __device__ __forceinline__ uint32_t mf_rol(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
 __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
+// The only op on the serial chain is the last one: rol(a,5) + T compiles to a single LEA.HI.
+// T = f + (e + K + W) depends on values that are at least one round old.
 #define MF_SHA_R(F, K, a, b, c, d, e, wt)            \
     {                                                \
-        e += mf_rol(a, 5) + (F) + (K) + (wt);        \
+        uint32_t t0_ = e + (K) + (wt);               \
+        uint32_t t1_ = (F) + t0_;                    \
+        e = mf_rol(a, 5) + t1_;                      \
         b = mf_rol(b, 30);                           \
     }
 #define MF_SHA_W(t) (w[(t) & 15] = mf_rol(w[((t) + 13) & 15] ^ w[((t) + 8) & 15] ^ w[((t) + 2) & 15] ^ w[(t) & 15], 1))
@@ -33,22 +37,29 @@ __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x,
 // registers and the 5-variable rotation is pure renaming.
 __device__ __forceinline__ void mf_sha1_compress(uint32_t h[5], uint32_t w[16]) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
+    // round constants held in registers the compiler cannot see through: otherwise it re-associates
+    // "+K" to the end of every round, i.e. onto the serial chain (LEA.HI -> VIADD instead of LEA.HI)
+    uint32_t k1, k2, k3, k4;
+    asm volatile("mov.u32 %0, 0x5A827999;" : "=r"(k1));
+    asm volatile("mov.u32 %0, 0x6ED9EBA1;" : "=r"(k2));
+    asm volatile("mov.u32 %0, 0x8F1BBCDC;" : "=r"(k3));
+    asm volatile("mov.u32 %0, 0xCA62C1D6;" : "=r"(k4));
 #define MF_R5(F, K, t, W0, W1, W2, W3, W4)               \
     MF_SHA_R(F(b, c, d), K, a, b, c, d, e, W0);          \
     MF_SHA_R(F(a, b, c), K, e, a, b, c, d, W1);          \
     MF_SHA_R(F(e, a, b), K, d, e, a, b, c, W2);          \
     MF_SHA_R(F(d, e, a), K, c, d, e, a, b, W3);          \
     MF_SHA_R(F(c, d, e), K, b, c, d, e, a, W4);
-    MF_R5(MF_F_CH, 0x5A827999u, 0, w[0], w[1], w[2], w[3], w[4])
-    MF_R5(MF_F_CH, 0x5A827999u, 5, w[5], w[6], w[7], w[8], w[9])
-    MF_R5(MF_F_CH, 0x5A827999u, 10, w[10], w[11], w[12], w[13], w[14])
-    MF_R5(MF_F_CH, 0x5A827999u, 15, w[15], MF_SHA_W(16), MF_SHA_W(17), MF_SHA_W(18), MF_SHA_W(19))
+    MF_R5(MF_F_CH, k1, 0, w[0], w[1], w[2], w[3], w[4])
+    MF_R5(MF_F_CH, k1, 5, w[5], w[6], w[7], w[8], w[9])
+    MF_R5(MF_F_CH, k1, 10, w[10], w[11], w[12], w[13], w[14])
+    MF_R5(MF_F_CH, k1, 15, w[15], MF_SHA_W(16), MF_SHA_W(17), MF_SHA_W(18), MF_SHA_W(19))
 #pragma unroll
-    for (int t = 20; t < 40; t += 5) { MF_R5(MF_F_PAR, 0x6ED9EBA1u, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
+    for (int t = 20; t < 40; t += 5) { MF_R5(MF_F_PAR, k2, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
 #pragma unroll
-    for (int t = 40; t < 60; t += 5) { MF_R5(MF_F_MAJ, 0x8F1BBCDCu, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
+    for (int t = 40; t < 60; t += 5) { MF_R5(MF_F_MAJ, k3, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
 #pragma unroll
-    for (int t = 60; t < 80; t += 5) { MF_R5(MF_F_PAR, 0xCA62C1D6u, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
+    for (int t = 60; t < 80; t += 5) { MF_R5(MF_F_PAR, k4, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
 #undef MF_R5
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
 }

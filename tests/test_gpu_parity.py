@@ -54,8 +54,9 @@ def test_golden_artifacts_and_reference_written_files(gpu_codec, golden):
     assert keys == [golden["data_json"]["objects"][n] for n in names]
     # files the REAL reference wrote (zlib level 3, single stream) decode on the GPU
     ref_files = [base64.b64decode(golden["artifacts"][n]["gz_b64"]) for n in names]
-    ref_files += [base64.b64decode(g["gz_b64"]) for g in golden["raw_blobs"].values()]
-    want = pickles + list(golden_inputs.raw_blobs().values())
+    raw = golden_inputs.raw_blobs()
+    ref_files += [base64.b64decode(golden["raw_blobs"][n]["gz_b64"]) for n in raw]
+    want = pickles + [raw[n] for n in raw]
     got = gpu_codec.unpack_batch(ref_files)
     for i, (w, g) in enumerate(zip(want, got)):
         assert not isinstance(g, Exception), (i, g)
