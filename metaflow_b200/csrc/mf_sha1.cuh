@@ -1,12 +1,19 @@
-// mf_sha1.cuh -- SHA-1 (FIPS 180-4) batch kernel for sm_100a: one lane per blob.
+// mf_sha1.cuh -- SHA-1 (FIPS 180-4) batch kernel for sm_100a.
 //
 // Replaces hashlib.sha1(blob).hexdigest() at metaflow/datastore/content_addressed_store.py:98.
-// SHA-1 is a serial chain over 64-byte blocks of ONE blob (Merkle-Damgard), so the only
-// parallelism is across blobs: lane i of the grid walks blob i.  The critical path per round
-// is rol(a,5) + (f+e+K+W) = SHF + IADD3 (two dependent ALU ops, 8 cycles on sm_100), i.e.
-// >= 640 cycles per 64-byte block per stream; aggregate throughput = streams x ~190 MB/s up
-// to the INT32 issue limit.  The next block's 64 bytes are prefetched into registers while the
-// current block is compressed, so HBM latency stays off the chain.
+// SHA-1 is a serial chain over the 64-byte blocks of ONE blob (Merkle-Damgard): the only
+// parallelism is across blobs, and the speed of one stream is set by the dependent chain
+//     a' = rol(a,5) + T,   T = f(b,c,d) + e + K + W          (one LEA.HI per round on the chain)
+// so everything that is NOT on the chain is moved off the consumer's instruction stream:
+//
+//   CTA = one producer warp + one consumer warp, 32 streams (one per lane of each warp)
+//   producer: stages 512 bytes per stream with COALESCED 16-byte cp.async (one page per request
+//             instead of 32 -- a lane-per-blob gather thrashes the TLB), byte-swaps, expands
+//             the message schedule W[0..79], adds K, and writes (K+W)[t][lane] to shared memory
+//             (also builds the padded tail blocks: 0x80, zeros, 64-bit bit length);
+//   consumer: per round only LDS(K+W) / LOP3(f) / IADD3(T) / LEA.HI(a') / SHF(rol30).
+//   Double-buffered through named barriers (bar.sync / bar.arrive, 64 threads).
+// Blobs are sorted by length (host side) so the 32 streams of a CTA finish together.
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -14,104 +21,159 @@
 struct MfHashDesc {
     const uint8_t *src;   // device pointer, 16-byte aligned
     uint64_t len;
+    uint32_t out_index;   // where the digest goes: digests + 20 * out_index
+    uint32_t pad;
 };
 
 __device__ __forceinline__ uint32_t mf_rol(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
 __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
-// The only op on the serial chain is the last one: rol(a,5) + T compiles to a single LEA.HI.
-// T = f + (e + K + W) depends on values that are at least one round old.
-#define MF_SHA_R(F, K, a, b, c, d, e, wt)            \
-    {                                                \
-        uint32_t t0_ = e + (K) + (wt);               \
-        uint32_t t1_ = (F) + t0_;                    \
-        e = mf_rol(a, 5) + t1_;                      \
-        b = mf_rol(b, 30);                           \
-    }
-#define MF_SHA_W(t) (w[(t) & 15] = mf_rol(w[((t) + 13) & 15] ^ w[((t) + 8) & 15] ^ w[((t) + 2) & 15] ^ w[(t) & 15], 1))
 #define MF_F_CH(b, c, d) ((d) ^ ((b) & ((c) ^ (d))))
 #define MF_F_PAR(b, c, d) ((b) ^ (c) ^ (d))
 #define MF_F_MAJ(b, c, d) (((b) & (c)) | ((d) & ((b) | (c))))
 
-// One compression of the 16 big-endian words in w[] into h[].  Fully unrolled so w[] lives in
-// registers and the 5-variable rotation is pure renaming.
-__device__ __forceinline__ void mf_sha1_compress(uint32_t h[5], uint32_t w[16]) {
-    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4];
-    // round constants held in registers the compiler cannot see through: otherwise it re-associates
-    // "+K" to the end of every round, i.e. onto the serial chain (LEA.HI -> VIADD instead of LEA.HI)
-    uint32_t k1, k2, k3, k4;
-    asm volatile("mov.u32 %0, 0x5A827999;" : "=r"(k1));
-    asm volatile("mov.u32 %0, 0x6ED9EBA1;" : "=r"(k2));
-    asm volatile("mov.u32 %0, 0x8F1BBCDC;" : "=r"(k3));
-    asm volatile("mov.u32 %0, 0xCA62C1D6;" : "=r"(k4));
-#define MF_R5(F, K, t, W0, W1, W2, W3, W4)               \
-    MF_SHA_R(F(b, c, d), K, a, b, c, d, e, W0);          \
-    MF_SHA_R(F(a, b, c), K, e, a, b, c, d, W1);          \
-    MF_SHA_R(F(e, a, b), K, d, e, a, b, c, W2);          \
-    MF_SHA_R(F(d, e, a), K, c, d, e, a, b, W3);          \
-    MF_SHA_R(F(c, d, e), K, b, c, d, e, a, W4);
-    MF_R5(MF_F_CH, k1, 0, w[0], w[1], w[2], w[3], w[4])
-    MF_R5(MF_F_CH, k1, 5, w[5], w[6], w[7], w[8], w[9])
-    MF_R5(MF_F_CH, k1, 10, w[10], w[11], w[12], w[13], w[14])
-    MF_R5(MF_F_CH, k1, 15, w[15], MF_SHA_W(16), MF_SHA_W(17), MF_SHA_W(18), MF_SHA_W(19))
-#pragma unroll
-    for (int t = 20; t < 40; t += 5) { MF_R5(MF_F_PAR, k2, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
-#pragma unroll
-    for (int t = 40; t < 60; t += 5) { MF_R5(MF_F_MAJ, k3, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
-#pragma unroll
-    for (int t = 60; t < 80; t += 5) { MF_R5(MF_F_PAR, k4, t, MF_SHA_W(t), MF_SHA_W(t + 1), MF_SHA_W(t + 2), MF_SHA_W(t + 3), MF_SHA_W(t + 4)) }
-#undef MF_R5
-    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e;
+#define MF_SHA_GROUP 512u                 // bytes staged per stream per group (8 blocks)
+#define MF_SHA_ROW (MF_SHA_GROUP + 16u)   // padded row: 16-byte reads of 8 consecutive lanes hit 8 distinct slots
+
+struct __align__(16) MfShaSmem {
+    uint8_t raw[2][32][MF_SHA_ROW];
+    uint32_t kw[2][80][32];
+};
+
+#define MF_BAR_FULL(b) (1 + (b))
+#define MF_BAR_EMPTY(b) (3 + (b))
+// barrier ids as immediates (a register id makes ptxas reserve all 16 hardware barriers per CTA)
+__device__ __forceinline__ void mf_bar_sync(int id) {
+    switch (id) {
+        case 1: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 3: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void mf_bar_arrive(int id) {
+    switch (id) {
+        case 1: asm volatile("bar.arrive 1, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.arrive 2, 64;" ::: "memory"); break;
+        case 3: asm volatile("bar.arrive 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.arrive 4, 64;" ::: "memory"); break;
+    }
 }
 
-__device__ __forceinline__ void mf_sha1_load_block(const uint4 *p, uint32_t w[16]) {
-    uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3);
-    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w;
-    w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
-    w[8] = v2.x; w[9] = v2.y; w[10] = v2.z; w[11] = v2.w;
-    w[12] = v3.x; w[13] = v3.y; w[14] = v3.z; w[15] = v3.w;
+__device__ __forceinline__ void mf_cp_async16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 
-// digests: 20 bytes per blob (big-endian words, i.e. the hashlib.sha1().digest() byte order)
-__global__ void __launch_bounds__(128) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint8_t *src = blobs[i].src;
-    uint64_t len = blobs[i].len;
-    uint32_t h[5] = {0x67452301u, 0xEFCDAB89u, 0x98BADCFEu, 0x10325476u, 0xC3D2E1F0u};
-    uint64_t nfull = len >> 6;
-    const uint4 *p = reinterpret_cast<const uint4 *>(src);
-    uint32_t w[16], nx[16];
-    if (nfull) mf_sha1_load_block(p, nx);
-    for (uint64_t b = 0; b < nfull; b++) {
+// digests: 20 bytes per blob in hashlib.sha1().digest() byte order
+__global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests) {
+    extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
+    MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t s = blockIdx.x * 32u + lane;
+    const bool valid = s < n;
+    const uint8_t *src = valid ? blobs[s].src : nullptr;
+    const uint64_t len = valid ? blobs[s].len : 0;
+    const uint64_t nfull = len >> 6;
+    const uint32_t r = (uint32_t)(len & 63u);
+    const uint64_t nb = valid ? nfull + (r < 56 ? 1 : 2) : 0;       // blocks incl. padding
+    uint64_t iters = nb;
 #pragma unroll
-        for (int k = 0; k < 16; k++) w[k] = mf_bswap(nx[k]);
-        if (b + 1 < nfull) mf_sha1_load_block(p + 4 * (b + 1), nx);   // prefetch next block
-        mf_sha1_compress(h, w);
-    }
-    // tail: remaining r < 64 bytes, then 0x80, zero pad, 64-bit big-endian bit length.
-    // Built in a separate (dynamically indexed, local-memory) array so that w[] above stays in registers.
-    uint32_t r = (uint32_t)(len & 63u);
-    const uint8_t *tp = src + (nfull << 6);
-    uint32_t tw[32];
+    for (int d = 16; d > 0; d >>= 1) { uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, iters, d); iters = o > iters ? o : iters; }
+
+    if (warp == 1) {
+        // ------------------------------------------------------------------ producer
+        const uint64_t ngroups = (iters + 7) >> 3;
+        auto issue_group = [&](uint64_t g) {
+            if (g < ngroups) {
+                const uint64_t off = g * MF_SHA_GROUP + lane * 16u;
+                for (int t = 0; t < 32; t++) {
+                    const uint8_t *p = (const uint8_t *)__shfl_sync(0xFFFFFFFFu, (unsigned long long)src, t);
+                    const uint64_t ln = __shfl_sync(0xFFFFFFFFu, (unsigned long long)len, t);
+                    uint32_t nbytes = 0;
+                    if (p && off < ln) nbytes = (ln - off) >= 16 ? 16u : (uint32_t)(ln - off);
+                    if (nbytes) mf_cp_async16(&S.raw[g & 1][t][lane * 16u], p + off, nbytes);
+                    else *reinterpret_cast<uint4 *>(&S.raw[g & 1][t][lane * 16u]) = make_uint4(0, 0, 0, 0);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue_group(0);
+        issue_group(1);
+        const uint64_t bits = len << 3;
+        for (uint64_t i = 0; i < iters; i++) {
+            const uint64_t g = i >> 3;
+            const int b = (int)(i & 1);
+            if ((i & 7) == 0) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); }
+            uint32_t w[16];
+            {
+                const uint4 *row = reinterpret_cast<const uint4 *>(&S.raw[g & 1][lane][(i & 7) * 64u]);
+                uint4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+                w[0] = mf_bswap(v0.x); w[1] = mf_bswap(v0.y); w[2] = mf_bswap(v0.z); w[3] = mf_bswap(v0.w);
+                w[4] = mf_bswap(v1.x); w[5] = mf_bswap(v1.y); w[6] = mf_bswap(v1.z); w[7] = mf_bswap(v1.w);
+                w[8] = mf_bswap(v2.x); w[9] = mf_bswap(v2.y); w[10] = mf_bswap(v2.z); w[11] = mf_bswap(v2.w);
+                w[12] = mf_bswap(v3.x); w[13] = mf_bswap(v3.y); w[14] = mf_bswap(v3.z); w[15] = mf_bswap(v3.w);
+            }
+            if (i >= nfull) {
+                // padding: bytes past the message are zero in the staging row already (cp.async zero-fill)
+                if (i == nfull) {
+                    const uint32_t marker = 0x80u << (24 - 8 * (r & 3)), rk = r >> 2;
 #pragma unroll
-    for (int k = 0; k < 32; k++) tw[k] = 0;
-    for (uint32_t k = 0; k < r; k++) tw[k >> 2] |= (uint32_t)tp[k] << (24 - 8 * (k & 3));
-    tw[r >> 2] |= 0x80u << (24 - 8 * (r & 3));
-    const uint64_t bits = len << 3;
-    const int nb = (r >= 56) ? 2 : 1;
-    tw[16 * nb - 2] = (uint32_t)(bits >> 32);
-    tw[16 * nb - 1] = (uint32_t)bits;
-    for (int blk = 0; blk < nb; blk++) {
-        uint32_t t2[16];
+                    for (int k = 0; k < 16; k++) w[k] |= marker & (0u - (uint32_t)(rk == (uint32_t)k));   // branch-free: keeps w[] in registers
+                }
+                if (i + 1 == nb) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
+            }
+            if (i >= 2) mf_bar_sync(MF_BAR_EMPTY(b));
+            uint32_t *kw = &S.kw[b][0][lane];
+#define MF_W(t) (w[(t) & 15] = mf_rol(w[((t) + 13) & 15] ^ w[((t) + 8) & 15] ^ w[((t) + 2) & 15] ^ w[(t) & 15], 1))
 #pragma unroll
-        for (int k = 0; k < 16; k++) t2[k] = tw[16 * blk + k];
-        mf_sha1_compress(h, t2);
-    }
-    uint8_t *out = digests + 20ull * i;
+            for (int t = 0; t < 16; t++) kw[t * 32] = w[t] + 0x5A827999u;
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        out[4 * k] = (uint8_t)(h[k] >> 24); out[4 * k + 1] = (uint8_t)(h[k] >> 16);
-        out[4 * k + 2] = (uint8_t)(h[k] >> 8); out[4 * k + 3] = (uint8_t)h[k];
+            for (int t = 16; t < 20; t++) kw[t * 32] = MF_W(t) + 0x5A827999u;
+#pragma unroll
+            for (int t = 20; t < 40; t++) kw[t * 32] = MF_W(t) + 0x6ED9EBA1u;
+#pragma unroll
+            for (int t = 40; t < 60; t++) kw[t * 32] = MF_W(t) + 0x8F1BBCDCu;
+#pragma unroll
+            for (int t = 60; t < 80; t++) kw[t * 32] = MF_W(t) + 0xCA62C1D6u;
+#undef MF_W
+            __threadfence_block();
+            mf_bar_arrive(MF_BAR_FULL(b));
+            if ((i & 7) == 7) { __syncwarp(); issue_group(g + 2); }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+        // ------------------------------------------------------------------ consumer
+        uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
+        for (uint64_t i = 0; i < iters; i++) {
+            const int bsel = (int)(i & 1);
+            mf_bar_sync(MF_BAR_FULL(bsel));
+            const uint32_t *kw = &S.kw[bsel][0][lane];
+            uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
+            // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI)
+#define MF_RND(F, a, b, c, d, e, t) { uint32_t t0_ = e + kw[(t) * 32]; uint32_t t1_ = F(b, c, d) + t0_; e = mf_rol(a, 5) + t1_; b = mf_rol(b, 30); }
+#define MF_RND5(F, t) MF_RND(F, a, b, c, d, e, t) MF_RND(F, e, a, b, c, d, (t) + 1) MF_RND(F, d, e, a, b, c, (t) + 2) MF_RND(F, c, d, e, a, b, (t) + 3) MF_RND(F, b, c, d, e, a, (t) + 4)
+#pragma unroll
+            for (int t = 0; t < 20; t += 5) { MF_RND5(MF_F_CH, t) }
+#pragma unroll
+            for (int t = 20; t < 40; t += 5) { MF_RND5(MF_F_PAR, t) }
+#pragma unroll
+            for (int t = 40; t < 60; t += 5) { MF_RND5(MF_F_MAJ, t) }
+#pragma unroll
+            for (int t = 60; t < 80; t += 5) { MF_RND5(MF_F_PAR, t) }
+#undef MF_RND5
+#undef MF_RND
+            if (i < nb) { h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; }
+            if (i + 2 < iters) mf_bar_arrive(MF_BAR_EMPTY(bsel));
+        }
+        if (valid) {
+            uint8_t *out = digests + 20ull * blobs[s].out_index;
+            const uint32_t hh[5] = {h0, h1, h2, h3, h4};
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                out[4 * k] = (uint8_t)(hh[k] >> 24); out[4 * k + 1] = (uint8_t)(hh[k] >> 16);
+                out[4 * k + 2] = (uint8_t)(hh[k] >> 8); out[4 * k + 3] = (uint8_t)hh[k];
+            }
+        }
     }
 }

@@ -112,6 +112,7 @@ int device_setup(DeviceState &D) {
     for (auto &e : D.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&D.ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&D.ev_sha, cudaEventDisableTiming));
+    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfShaSmem)));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     mf_init_tables_kernel<<<2, 256, 0, D.stream>>>();
@@ -161,9 +162,19 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
     uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
     uint32_t mi = 0, ci = 0;
+    {   // SHA-1 streams sorted by length (descending): the 32 streams of a CTA then finish together
+        std::vector<uint32_t> order(n);
+        for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
+        for (uint64_t k = 0; k < n; k++) {
+            const uint32_t i = order[k];
+            h_hash[k].src = static_cast<const uint8_t *>(d_src[i]);
+            h_hash[k].len = src_len[i];
+            h_hash[k].out_index = i;
+            h_hash[k].pad = 0;
+        }
+    }
     for (uint64_t i = 0; i < n; i++) {
-        h_hash[i].src = static_cast<const uint8_t *>(d_src[i]);
-        h_hash[i].len = src_len[i];
         if (!want_pack) continue;
         h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
         h_blob[i].dst_cap = dst_cap[i];
@@ -211,7 +222,7 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     // ---- SHA-1 on the second stream (serial per blob, so it overlaps the chunk-parallel encoder)
     CU(cudaStreamWaitEvent(s2, D.ev_in, 0));
     CU(cudaEventRecord(D.ev[0], s2));
-    mf_sha1_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
+    mf_sha1_kernel<<<(unsigned)((n + 31) / 32), 64, sizeof(MfShaSmem), s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(D.ev[1], s2));
