@@ -120,12 +120,16 @@ struct __align__(16) MfEncSmem {
 __global__ void __launch_bounds__(MF_ENC_THREADS, 2)
 mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__restrict__ chunk_member, uint32_t n_chunks_total,
                   uint8_t *__restrict__ slots, uint32_t *__restrict__ comp_bytes_out, uint16_t *__restrict__ hdr_bits_out,
-                  uint16_t *__restrict__ seg_bits_out, uint32_t *__restrict__ chunk_crc_out, uint32_t flags) {
+                  uint16_t *__restrict__ seg_bits_out, uint32_t *__restrict__ chunk_crc_out, uint32_t flags,
+                  unsigned long long *__restrict__ phase_clk) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfEncSmem &S = *reinterpret_cast<MfEncSmem *>(mf_smem_raw);
     const uint32_t c = blockIdx.x;
     if (c >= n_chunks_total) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
+#define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 8 + (k)] = clock64(); } while (0)
+    MF_PHASE(0);
     const MfEncMember mem = members[chunk_member[c]];
     const uint32_t ci = c - mem.first_chunk;
     const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
@@ -148,6 +152,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     if (tid < 16 && (len & 15u) && tid >= (len & 15u)) S.data[(len & ~15u) + tid] = 0;
     __syncthreads();
 
+    MF_PHASE(1);
     // ---- pass 1: CRC-32 (raw, zero init) of the chunk; piece g = 64 bytes [64g, 64g+64)
     {
         uint32_t g = tid;                       // 512 pieces
@@ -166,6 +171,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
         if (lane == 0) S.crc_part[warp] = crc;
     }
 
+    MF_PHASE(2);
     // ---- pass 2: LZ77 over this warp's two segments
     {
         uint16_t *ht = reinterpret_cast<uint16_t *>(S.regionB) + warp * (1u << MF_HASH_BITS);
@@ -255,6 +261,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     if (tid == 0) S.ll_hist[256] = 1;       // end-of-block
     __syncthreads();
 
+    MF_PHASE(3);
     // ---- pass 3: Huffman codes, block header
     mf_huff_build<512>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.huff);
     mf_huff_build<32>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.huff);
@@ -269,6 +276,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     if (tid == 0) mf_hdr_write(outw, S.hdr);
     __syncthreads();
 
+    MF_PHASE(4);
     // ---- pass 4: bit counts per lane, per segment
     for (uint32_t si = 0; si < 2; si++) {
         const uint32_t seg = warp * 2 + si;
@@ -299,6 +307,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     }
     __syncthreads();
 
+    MF_PHASE(5);
     // ---- pass 5: pack
     if (!S.stored) {
         for (uint32_t si = 0; si < 2; si++) {
@@ -342,6 +351,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     }
     __syncthreads();
 
+    MF_PHASE(6);
     // ---- write out: slot bytes, index entries, chunk CRC
     {
         const uint32_t cb = S.comp_bytes;
@@ -357,6 +367,8 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
             chunk_crc_out[c] = crc;
         }
     }
+    MF_PHASE(7);
+#undef MF_PHASE
 }
 
 // ------------------------------------------------------------------ gather: members -> final bytes

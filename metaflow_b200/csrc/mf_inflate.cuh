@@ -154,6 +154,7 @@ struct MfFastReader {
     const uint32_t *w;
     uint64_t buf;
     uint32_t cnt;
+    uint32_t nxt;    // word loaded one refill ahead: its L2 latency hides behind ~32 bits of decoding
     uint64_t used;   // bits consumed since init
     __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos) {
         const uint8_t *a = src + (bitpos >> 3);
@@ -163,9 +164,10 @@ struct MfFastReader {
         buf = (uint64_t)__ldg(w++) >> skip;
         cnt = 32u - skip;
         buf |= (uint64_t)__ldg(w++) << cnt; cnt += 32u;
+        nxt = __ldg(w++);
         used = 0;
     }
-    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)__ldg(w++) << cnt; cnt += 32u; } }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)nxt << cnt; cnt += 32u; nxt = __ldg(w++); } }
     __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }   // k <= 16, call fill() first
     __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; used += k; }
     __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }

@@ -151,7 +151,12 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
             const uint32_t *kw = &S.kw[bsel][0][lane];
             uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
             // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI)
-#define MF_RND(F, a, b, c, d, e, t) { uint32_t t0_ = e + kw[(t) * 32]; uint32_t t1_ = F(b, c, d) + t0_; e = mf_rol(a, 5) + t1_; b = mf_rol(b, 30); }
+// The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the rotate-add
+// and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
+#define MF_RND(F, a, b, c, d, e, t) { uint32_t f_ = F(b, c, d); uint32_t kw_ = kw[(t) * 32]; \
+        asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
+            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
+        b = mf_rol(b, 30); }
 #define MF_RND5(F, t) MF_RND(F, a, b, c, d, e, t) MF_RND(F, e, a, b, c, d, (t) + 1) MF_RND(F, d, e, a, b, c, (t) + 2) MF_RND(F, c, d, e, a, b, (t) + 3) MF_RND(F, b, c, d, e, a, (t) + 4)
 #pragma unroll
             for (int t = 0; t < 20; t += 5) { MF_RND5(MF_F_CH, t) }

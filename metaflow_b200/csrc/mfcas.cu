@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <mutex>
@@ -66,7 +67,7 @@ struct DeviceState {
     // wave arenas (host-pointer API)
     DevBuf in_arena, out_arena;
     // descriptors / results
-    DevBuf d_desc, d_work, slots;
+    DevBuf d_desc, d_work, slots, phase;
     HostBuf h_desc, h_res;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -108,11 +109,15 @@ struct Carver {
 int device_setup(DeviceState &D) {
     CU(cudaSetDevice(D.dev));
     CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&D.stream2, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&D.stream2, cudaStreamNonBlocking, hi));   // SHA-1 CTAs are dispatched first
+    }
     for (auto &e : D.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&D.ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&D.ev_sha, cudaEventDisableTiming));
-    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfShaSmem)));
+    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     mf_init_tables_kernel<<<2, 256, 0, D.stream>>>();
@@ -126,7 +131,7 @@ void device_teardown(DeviceState &D) {
     cudaSetDevice(D.dev);
     if (D.stream) cudaStreamSynchronize(D.stream);
     if (D.stream2) cudaStreamSynchronize(D.stream2);
-    D.in_arena.release(); D.out_arena.release(); D.d_desc.release(); D.d_work.release(); D.slots.release();
+    D.in_arena.release(); D.out_arena.release(); D.d_desc.release(); D.d_work.release(); D.slots.release(); D.phase.release();
     D.h_desc.release(); D.h_res.release();
     for (auto &e : D.ev) if (e) cudaEventDestroy(e);
     if (D.ev_in) cudaEventDestroy(D.ev_in);
@@ -215,6 +220,12 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     uint8_t *dres = dw + o_res;
 
     cudaStream_t s = D.stream, s2 = D.stream2;
+    unsigned long long *phase = nullptr;      // MFCAS_PHASE_TIMING=1: per-chunk clock64 at phase boundaries
+    static const bool phase_on = getenv("MFCAS_PHASE_TIMING") != nullptr;
+    if (phase_on && want_pack && n_chunks) {
+        CU(D.phase.ensure(n_chunks * 8 * sizeof(unsigned long long)));
+        phase = D.phase.as<unsigned long long>();
+    }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(dres + r_st, 0, sizeof(int32_t) * n, s));
     CU(cudaEventRecord(D.ev_in, s));
@@ -222,7 +233,12 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     // ---- SHA-1 on the second stream (serial per blob, so it overlaps the chunk-parallel encoder)
     CU(cudaStreamWaitEvent(s2, D.ev_in, 0));
     CU(cudaEventRecord(D.ev[0], s2));
-    mf_sha1_kernel<<<(unsigned)((n + 31) / 32), 64, sizeof(MfShaSmem), s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
+    // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
+    // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
+    // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
+    const unsigned sha_ctas = (unsigned)((n + 31) / 32);
+    const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
+    mf_sha1_kernel<<<sha_ctas, 64, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(D.ev[1], s2));
@@ -233,7 +249,7 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
             mf_deflate_kernel<<<(unsigned)n_chunks, MF_ENC_THREADS, sizeof(MfEncSmem), s>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 D.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
-                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags);
+                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase);
             CU(cudaGetLastError());
             D.launches++;
         }
@@ -269,6 +285,17 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
         for (uint64_t i = 0; i < n; i++) status[i] = 0;
     }
     cudaEventElapsedTime(&D.ms[0], D.ev[0], D.ev[1]);
+    if (phase) {
+        std::vector<unsigned long long> h(n_chunks * 8);
+        CU(cudaMemcpy(h.data(), phase, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double acc[7] = {0};
+        for (uint64_t c = 0; c < n_chunks; c++)
+            for (int k = 0; k < 7; k++) acc[k] += (double)(h[c * 8 + k + 1] - h[c * 8 + k]);
+        static const char *nm[7] = {"load", "crc", "lz77", "huffman+header", "bitcount", "pack", "store"};
+        fprintf(stderr, "[mfcas phase] deflate, mean cycles per chunk over %llu chunks:", (unsigned long long)n_chunks);
+        for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)n_chunks);
+        fprintf(stderr, "\n");
+    }
     return MFCAS_OK;
 }
 
