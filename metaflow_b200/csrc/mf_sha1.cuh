@@ -137,7 +137,8 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
 #pragma unroll
             for (int t = 60; t < 80; t++) kw[t * 32] = MF_W(t) + 0xCA62C1D6u;
 #undef MF_W
-            __threadfence_block();
+            // no fence: bar.arrive orders this thread's prior shared-memory stores for the barrier's
+            // participants (the PTX producer/consumer idiom); a MEMBAR here would drain 80 STS per block
             mf_bar_arrive(MF_BAR_FULL(b));
             if ((i & 7) == 7) { __syncwarp(); issue_group(g + 2); }
         }
