@@ -128,7 +128,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     if (c >= n_chunks_total) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
-#define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 8 + (k)] = clock64(); } while (0)
+#define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 16 + (k)] = clock64(); } while (0)
     MF_PHASE(0);
     const MfEncMember mem = members[chunk_member[c]];
     const uint32_t ci = c - mem.first_chunk;
@@ -264,16 +264,22 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     MF_PHASE(3);
     // ---- pass 3: Huffman codes, block header
     mf_huff_build<512>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.huff);
+    MF_PHASE(8);
     mf_huff_build<32>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.huff);
+    MF_PHASE(9);
     if (tid == 0) mf_hdr_rle(S.ll_lens, S.d_lens, S.hdr);
+    MF_PHASE(10);
     {   // region B is dead as hash tables now: zero it for the bit writers
         uint4 *z = reinterpret_cast<uint4 *>(S.regionB);
         for (uint32_t i = tid; i < MF_REGION_B / 16; i += MF_ENC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
+    MF_PHASE(11);
     mf_huff_build<32>(S.hdr.clhist, 19, 7, S.hdr.cllens, S.hdr.clcodes, S.huff);
+    MF_PHASE(12);
     uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
     if (tid == 0) mf_hdr_write(outw, S.hdr);
+    MF_PHASE(13);
     __syncthreads();
 
     MF_PHASE(4);

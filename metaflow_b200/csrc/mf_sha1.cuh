@@ -66,7 +66,8 @@ __device__ __forceinline__ void mf_cp_async16(void *smem_dst, const void *gsrc, 
 }
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order
-__global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests) {
+__global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
+                                                      unsigned long long *__restrict__ dbg) {
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
         issue_group(0);
         issue_group(1);
         const uint64_t bits = len << 3;
+        long long pwait = 0, pstart = dbg ? clock64() : 0;
         for (uint64_t i = 0; i < iters; i++) {
             const uint64_t g = i >> 3;
             const int b = (int)(i & 1);
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
                 }
                 if (i + 1 == nb) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
             }
-            if (i >= 2) mf_bar_sync(MF_BAR_EMPTY(b));
+            if (i >= 2) { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_EMPTY(b)); if (dbg) pwait += clock64() - t0_; }
             uint32_t *kw = &S.kw[b][0][lane];
 #define MF_W(t) (w[(t) & 15] = mf_rol(w[((t) + 13) & 15] ^ w[((t) + 8) & 15] ^ w[((t) + 2) & 15] ^ w[(t) & 15], 1))
 #pragma unroll
@@ -143,12 +145,14 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
             if ((i & 7) == 7) { __syncwarp(); issue_group(g + 2); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (dbg && lane == 0) { dbg[blockIdx.x * 4 + 0] = (unsigned long long)pwait; dbg[blockIdx.x * 4 + 1] = (unsigned long long)(clock64() - pstart); }
     } else {
         // ------------------------------------------------------------------ consumer
         uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
+        long long cwait = 0, cstart = dbg ? clock64() : 0;
         for (uint64_t i = 0; i < iters; i++) {
             const int bsel = (int)(i & 1);
-            mf_bar_sync(MF_BAR_FULL(bsel));
+            { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_FULL(bsel)); if (dbg) cwait += clock64() - t0_; }
             const uint32_t *kw = &S.kw[bsel][0][lane];
             uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
             // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI)
@@ -172,6 +176,7 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
             if (i < nb) { h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; }
             if (i + 2 < iters) mf_bar_arrive(MF_BAR_EMPTY(bsel));
         }
+        if (dbg && lane == 0) { dbg[blockIdx.x * 4 + 2] = (unsigned long long)cwait; dbg[blockIdx.x * 4 + 3] = (unsigned long long)(clock64() - cstart); }
         if (valid) {
             uint8_t *out = digests + 20ull * blobs[s].out_index;
             const uint32_t hh[5] = {h0, h1, h2, h3, h4};

@@ -67,7 +67,7 @@ struct DeviceState {
     // wave arenas (host-pointer API)
     DevBuf in_arena, out_arena;
     // descriptors / results
-    DevBuf d_desc, d_work, slots, phase;
+    DevBuf d_desc, d_work, slots, phase, phase2;
     HostBuf h_desc, h_res;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -223,7 +223,8 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     unsigned long long *phase = nullptr;      // MFCAS_PHASE_TIMING=1: per-chunk clock64 at phase boundaries
     static const bool phase_on = getenv("MFCAS_PHASE_TIMING") != nullptr;
     if (phase_on && want_pack && n_chunks) {
-        CU(D.phase.ensure(n_chunks * 8 * sizeof(unsigned long long)));
+        CU(D.phase.ensure(n_chunks * 16 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(D.phase.p, 0, n_chunks * 16 * sizeof(unsigned long long), D.stream));
         phase = D.phase.as<unsigned long long>();
     }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
@@ -238,7 +239,9 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
     const unsigned sha_ctas = (unsigned)((n + 31) / 32);
     const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
-    mf_sha1_kernel<<<sha_ctas, 64, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha);
+    unsigned long long *sha_dbg = nullptr;
+    if (phase_on) { CU(D.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = D.phase2.as<unsigned long long>(); }
+    mf_sha1_kernel<<<sha_ctas, 64, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha, sha_dbg);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(D.ev[1], s2));
@@ -285,15 +288,25 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
         for (uint64_t i = 0; i < n; i++) status[i] = 0;
     }
     cudaEventElapsedTime(&D.ms[0], D.ev[0], D.ev[1]);
+    if (sha_dbg) {
+        std::vector<unsigned long long> h((size_t)sha_ctas * 4);
+        CU(cudaMemcpy(h.data(), sha_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        double a[4] = {0};
+        for (unsigned c = 0; c < sha_ctas; c++) for (int k = 0; k < 4; k++) a[k] += (double)h[c * 4 + k];
+        fprintf(stderr, "[mfcas phase] sha1 over %u CTAs: producer wait=%.0f total=%.0f | consumer wait=%.0f total=%.0f cycles\n", sha_ctas,
+                a[0] / sha_ctas, a[1] / sha_ctas, a[2] / sha_ctas, a[3] / sha_ctas);
+    }
     if (phase) {
-        std::vector<unsigned long long> h(n_chunks * 8);
+        std::vector<unsigned long long> h(n_chunks * 16);
         CU(cudaMemcpy(h.data(), phase, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        double acc[7] = {0};
+        // boundaries in program order: 0 start,1 loaded,2 crc done,3 lz done,8 litlen code,9 dist code,10 rle,11 zeroed+sync,12 cl code,13 header,4 ... 7
+        static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
+        static const char *nm[13] = {"load", "crc", "lz77", "litlen_code", "dist_code", "hdr_rle", "zero+sync", "cl_code", "hdr_write", "sync", "bitcount", "pack", "store"};
+        double acc[13] = {0};
         for (uint64_t c = 0; c < n_chunks; c++)
-            for (int k = 0; k < 7; k++) acc[k] += (double)(h[c * 8 + k + 1] - h[c * 8 + k]);
-        static const char *nm[7] = {"load", "crc", "lz77", "huffman+header", "bitcount", "pack", "store"};
+            for (int k = 0; k < 13; k++) acc[k] += (double)(h[c * 16 + seq[k + 1]] - h[c * 16 + seq[k]]);
         fprintf(stderr, "[mfcas phase] deflate, mean cycles per chunk over %llu chunks:", (unsigned long long)n_chunks);
-        for (int k = 0; k < 7; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)n_chunks);
+        for (int k = 0; k < 13; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)n_chunks);
         fprintf(stderr, "\n");
     }
     return MFCAS_OK;
