@@ -156,7 +156,7 @@ def run_ours(args, rank, world, local_rank):
         dist_mod.init_process_group("nccl", device_id=dev)
         dist = dist_mod
     devs = (ctypes.c_int * 1)(local_rank)
-    ctx = lib.mfcas_create(devs, 1, args.wave_gib << 30, 0)
+    ctx = lib.mfcas_create(devs, 1, args.wave_mib << 20, 0)
     if not ctx:
         raise SystemExit("mfcas_create failed: no CUDA device -- the hot path has no CPU fallback")
     ctx = ctypes.c_void_p(ctx)
@@ -370,7 +370,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blobs-per-step", type=int, default=512)
-    ap.add_argument("--wave-gib", type=int, default=24, help="device arena per wave for the host-pointer API")
+    ap.add_argument("--wave-mib", type=int, default=2048, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -6,13 +6,13 @@
 //     a' = rol(a,5) + T,   T = f(b,c,d) + e + K + W          (one LEA.HI per round on the chain)
 // so everything that is NOT on the chain is moved off the consumer's instruction stream:
 //
-//   CTA = one producer warp + one consumer warp, 32 streams (one per lane of each warp)
+//   CTA = one consumer warp + two producer warps (even / odd blocks), 32 streams (one per lane)
 //   producer: stages 512 bytes per stream with COALESCED 16-byte cp.async (one page per request
 //             instead of 32 -- a lane-per-blob gather thrashes the TLB), byte-swaps, expands
 //             the message schedule W[0..79], adds K, and writes (K+W)[t][lane] to shared memory
 //             (also builds the padded tail blocks: 0x80, zeros, 64-bit bit length);
 //   consumer: per round only LDS(K+W) / LOP3(f) / IADD3(T) / LEA.HI(a') / SHF(rol30).
-//   Double-buffered through named barriers (bar.sync / bar.arrive, 64 threads).
+//   Buffer b belongs to producer b; hand-over through named barriers (bar.sync / bar.arrive, 64 threads).
 // Blobs are sorted by length (host side) so the 32 streams of a CTA finish together.
 #pragma once
 #include <stdint.h>
@@ -35,9 +35,11 @@ __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x,
 #define MF_SHA_GROUP 512u                 // bytes staged per stream per group (8 blocks)
 #define MF_SHA_ROW (MF_SHA_GROUP + 16u)   // padded row: 16-byte reads of 8 consecutive lanes hit 8 distinct slots
 
+#define MF_SHA_KWROW 84u                  // words per lane row of (K+W): 80 + 4 pad -> 16-byte accesses of 8 lanes are conflict-free
+
 struct __align__(16) MfShaSmem {
-    uint8_t raw[2][32][MF_SHA_ROW];
-    uint32_t kw[2][80][32];
+    uint8_t raw[2][2][32][MF_SHA_ROW];    // [producer][group parity][stream][bytes]
+    uint32_t kw[2][32][MF_SHA_KWROW];     // [buffer = producer][stream][round]
 };
 
 #define MF_BAR_FULL(b) (1 + (b))
@@ -66,7 +68,7 @@ __device__ __forceinline__ void mf_cp_async16(void *smem_dst, const void *gsrc, 
 }
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order
-__global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
+__global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
                                                       unsigned long long *__restrict__ dbg) {
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, iters, d); iters = o > iters ? o : iters; }
 
-    if (warp == 1) {
-        // ------------------------------------------------------------------ producer
+    if (warp >= 1) {
+        // ------------------------------------------------------------------ producers (warp 1: even blocks, warp 2: odd blocks)
+        const uint32_t pid = warp - 1;
         const uint64_t ngroups = (iters + 7) >> 3;
         auto issue_group = [&](uint64_t g) {
             if (g < ngroups) {
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
                     const uint64_t ln = __shfl_sync(0xFFFFFFFFu, (unsigned long long)len, t);
                     uint32_t nbytes = 0;
                     if (p && off < ln) nbytes = (ln - off) >= 16 ? 16u : (uint32_t)(ln - off);
-                    if (nbytes) mf_cp_async16(&S.raw[g & 1][t][lane * 16u], p + off, nbytes);
-                    else *reinterpret_cast<uint4 *>(&S.raw[g & 1][t][lane * 16u]) = make_uint4(0, 0, 0, 0);
+                    if (nbytes) mf_cp_async16(&S.raw[pid][g & 1][t][lane * 16u], p + off, nbytes);
+                    else *reinterpret_cast<uint4 *>(&S.raw[pid][g & 1][t][lane * 16u]) = make_uint4(0, 0, 0, 0);
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -103,13 +106,14 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
         issue_group(1);
         const uint64_t bits = len << 3;
         long long pwait = 0, pstart = dbg ? clock64() : 0;
-        for (uint64_t i = 0; i < iters; i++) {
+        const int b = (int)pid;
+        uint64_t cur_group = ~0ull;
+        for (uint64_t i = pid; i < iters; i += 2) {
             const uint64_t g = i >> 3;
-            const int b = (int)(i & 1);
-            if ((i & 7) == 0) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); }
+            if (g != cur_group) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); cur_group = g; }
             uint32_t w[16];
             {
-                const uint4 *row = reinterpret_cast<const uint4 *>(&S.raw[g & 1][lane][(i & 7) * 64u]);
+                const uint4 *row = reinterpret_cast<const uint4 *>(&S.raw[pid][g & 1][lane][(i & 7) * 64u]);
                 uint4 v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
                 w[0] = mf_bswap(v0.x); w[1] = mf_bswap(v0.y); w[2] = mf_bswap(v0.z); w[3] = mf_bswap(v0.w);
                 w[4] = mf_bswap(v1.x); w[5] = mf_bswap(v1.y); w[6] = mf_bswap(v1.z); w[7] = mf_bswap(v1.w);
@@ -126,26 +130,26 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
                 if (i + 1 == nb) { w[14] = (uint32_t)(bits >> 32); w[15] = (uint32_t)bits; }
             }
             if (i >= 2) { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_EMPTY(b)); if (dbg) pwait += clock64() - t0_; }
-            uint32_t *kw = &S.kw[b][0][lane];
+            uint4 *kw = reinterpret_cast<uint4 *>(&S.kw[b][lane][0]);
 #define MF_W(t) (w[(t) & 15] = mf_rol(w[((t) + 13) & 15] ^ w[((t) + 8) & 15] ^ w[((t) + 2) & 15] ^ w[(t) & 15], 1))
 #pragma unroll
-            for (int t = 0; t < 16; t++) kw[t * 32] = w[t] + 0x5A827999u;
+            for (int t = 0; t < 16; t += 4) kw[t >> 2] = make_uint4(w[t] + 0x5A827999u, w[t + 1] + 0x5A827999u, w[t + 2] + 0x5A827999u, w[t + 3] + 0x5A827999u);
+            { uint32_t a0 = MF_W(16), a1 = MF_W(17), a2 = MF_W(18), a3 = MF_W(19); kw[4] = make_uint4(a0 + 0x5A827999u, a1 + 0x5A827999u, a2 + 0x5A827999u, a3 + 0x5A827999u); }
 #pragma unroll
-            for (int t = 16; t < 20; t++) kw[t * 32] = MF_W(t) + 0x5A827999u;
+            for (int t = 20; t < 40; t += 4) { uint32_t a0 = MF_W(t), a1 = MF_W(t + 1), a2 = MF_W(t + 2), a3 = MF_W(t + 3); kw[t >> 2] = make_uint4(a0 + 0x6ED9EBA1u, a1 + 0x6ED9EBA1u, a2 + 0x6ED9EBA1u, a3 + 0x6ED9EBA1u); }
 #pragma unroll
-            for (int t = 20; t < 40; t++) kw[t * 32] = MF_W(t) + 0x6ED9EBA1u;
+            for (int t = 40; t < 60; t += 4) { uint32_t a0 = MF_W(t), a1 = MF_W(t + 1), a2 = MF_W(t + 2), a3 = MF_W(t + 3); kw[t >> 2] = make_uint4(a0 + 0x8F1BBCDCu, a1 + 0x8F1BBCDCu, a2 + 0x8F1BBCDCu, a3 + 0x8F1BBCDCu); }
 #pragma unroll
-            for (int t = 40; t < 60; t++) kw[t * 32] = MF_W(t) + 0x8F1BBCDCu;
-#pragma unroll
-            for (int t = 60; t < 80; t++) kw[t * 32] = MF_W(t) + 0xCA62C1D6u;
+            for (int t = 60; t < 80; t += 4) { uint32_t a0 = MF_W(t), a1 = MF_W(t + 1), a2 = MF_W(t + 2), a3 = MF_W(t + 3); kw[t >> 2] = make_uint4(a0 + 0xCA62C1D6u, a1 + 0xCA62C1D6u, a2 + 0xCA62C1D6u, a3 + 0xCA62C1D6u); }
 #undef MF_W
             // no fence: bar.arrive orders this thread's prior shared-memory stores for the barrier's
-            // participants (the PTX producer/consumer idiom); a MEMBAR here would drain 80 STS per block
+            // participants (the PTX producer/consumer idiom); a MEMBAR here would drain every store
             mf_bar_arrive(MF_BAR_FULL(b));
-            if ((i & 7) == 7) { __syncwarp(); issue_group(g + 2); }
+            // this producer is done with group g once it has taken its last block of it (blocks 6 or 7)
+            if ((i & 7) >= 6) { __syncwarp(); issue_group(g + 2); }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        if (dbg && lane == 0) { dbg[blockIdx.x * 4 + 0] = (unsigned long long)pwait; dbg[blockIdx.x * 4 + 1] = (unsigned long long)(clock64() - pstart); }
+        if (dbg && lane == 0 && pid == 0) { dbg[blockIdx.x * 4 + 0] = (unsigned long long)pwait; dbg[blockIdx.x * 4 + 1] = (unsigned long long)(clock64() - pstart); }
     } else {
         // ------------------------------------------------------------------ consumer
         uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
@@ -153,25 +157,26 @@ __global__ void __launch_bounds__(64) mf_sha1_kernel(const MfHashDesc *__restric
         for (uint64_t i = 0; i < iters; i++) {
             const int bsel = (int)(i & 1);
             { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_FULL(bsel)); if (dbg) cwait += clock64() - t0_; }
-            const uint32_t *kw = &S.kw[bsel][0][lane];
+            const uint4 *kwv = reinterpret_cast<const uint4 *>(&S.kw[bsel][lane][0]);
             uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
-            // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI)
-// The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the rotate-add
-// and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
-#define MF_RND(F, a, b, c, d, e, t) { uint32_t f_ = F(b, c, d); uint32_t kw_ = kw[(t) * 32]; \
+            // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI).
+            // The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the
+            // rotate-add and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
+#define MF_RND(F, a, b, c, d, e, kw_) { uint32_t f_ = F(b, c, d); \
         asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
             : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
         b = mf_rol(b, 30); }
-#define MF_RND5(F, t) MF_RND(F, a, b, c, d, e, t) MF_RND(F, e, a, b, c, d, (t) + 1) MF_RND(F, d, e, a, b, c, (t) + 2) MF_RND(F, c, d, e, a, b, (t) + 3) MF_RND(F, b, c, d, e, a, (t) + 4)
-#pragma unroll
-            for (int t = 0; t < 20; t += 5) { MF_RND5(MF_F_CH, t) }
-#pragma unroll
-            for (int t = 20; t < 40; t += 5) { MF_RND5(MF_F_PAR, t) }
-#pragma unroll
-            for (int t = 40; t < 60; t += 5) { MF_RND5(MF_F_MAJ, t) }
-#pragma unroll
-            for (int t = 60; t < 80; t += 5) { MF_RND5(MF_F_PAR, t) }
-#undef MF_RND5
+#define MF_RND20(F, q) { \
+        uint4 k0 = kwv[5 * (q)], k1 = kwv[5 * (q) + 1], k2 = kwv[5 * (q) + 2], k3 = kwv[5 * (q) + 3], k4 = kwv[5 * (q) + 4]; \
+        MF_RND(F, a, b, c, d, e, k0.x) MF_RND(F, e, a, b, c, d, k0.y) MF_RND(F, d, e, a, b, c, k0.z) MF_RND(F, c, d, e, a, b, k0.w) MF_RND(F, b, c, d, e, a, k1.x) \
+        MF_RND(F, a, b, c, d, e, k1.y) MF_RND(F, e, a, b, c, d, k1.z) MF_RND(F, d, e, a, b, c, k1.w) MF_RND(F, c, d, e, a, b, k2.x) MF_RND(F, b, c, d, e, a, k2.y) \
+        MF_RND(F, a, b, c, d, e, k2.z) MF_RND(F, e, a, b, c, d, k2.w) MF_RND(F, d, e, a, b, c, k3.x) MF_RND(F, c, d, e, a, b, k3.y) MF_RND(F, b, c, d, e, a, k3.z) \
+        MF_RND(F, a, b, c, d, e, k3.w) MF_RND(F, e, a, b, c, d, k4.x) MF_RND(F, d, e, a, b, c, k4.y) MF_RND(F, c, d, e, a, b, k4.z) MF_RND(F, b, c, d, e, a, k4.w) }
+            MF_RND20(MF_F_CH, 0)
+            MF_RND20(MF_F_PAR, 1)
+            MF_RND20(MF_F_MAJ, 2)
+            MF_RND20(MF_F_PAR, 3)
+#undef MF_RND20
 #undef MF_RND
             if (i < nb) { h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; }
             if (i + 2 < iters) mf_bar_arrive(MF_BAR_EMPTY(bsel));

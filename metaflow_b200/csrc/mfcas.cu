@@ -59,16 +59,32 @@ struct HostBuf {     // pinned
     template <typename T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
-struct DeviceState {
-    int dev = -1;
+enum class Op { Pack, Hash, Unpack };
+
+// One in-flight wave: its own streams, events and buffers, so that several waves overlap on the device
+// (H2D of wave k+1 | kernels of wave k | D2H of wave k-1; the serial SHA-1 kernels of many waves co-run).
+struct WaveCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_in = nullptr, ev_sha = nullptr;
-    // wave arenas (host-pointer API)
-    DevBuf in_arena, out_arena;
-    // descriptors / results
-    DevBuf d_desc, d_work, slots, phase, phase2;
+    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_res = nullptr, ev_done = nullptr;
+    DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2;
     HostBuf h_desc, h_res;
+    // bookkeeping of the submitted wave
+    int state = 0;                       // 0 idle, 1 kernels in flight, 2 output D2H in flight
+    Op op = Op::Pack;
+    uint64_t n = 0, n_chunks = 0;
+    unsigned sha_ctas = 0;
+    size_t r_len = 0, r_st = 0, r_sha = 0, res_bytes = 0;
+    bool timed_pack = false;
+    size_t pos = 0, wn = 0;              // slice [pos, pos+wn) of the shard (host-pointer API)
+    std::vector<const void *> w_src; std::vector<void *> w_dst;
+    std::vector<uint64_t> w_len, w_cap, w_dlen, w_ioff, w_ooff;
+    std::vector<int32_t> w_st; std::vector<uint8_t> w_sha;
+};
+
+struct DeviceState {
+    int dev = -1;
+    std::vector<WaveCtx> ring;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
     float ms[8] = {};
@@ -106,49 +122,58 @@ struct Carver {
     size_t take(size_t bytes, size_t align = 256) { off = align_up(off, align); size_t o = off; off += bytes; return o; }
 };
 
+#define MF_RING 8
+
+int wave_setup(DeviceState &D, WaveCtx &W) {
+    int lo = 0, hi = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithPriority(&W.stream2, cudaStreamNonBlocking, hi));   // SHA-1 CTAs are dispatched first
+    for (auto &e : W.ev) CU(cudaEventCreate(&e));
+    CU(cudaEventCreateWithFlags(&W.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&W.ev_sha, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&W.ev_res, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
+    return MFCAS_OK;
+}
+
 int device_setup(DeviceState &D) {
     CU(cudaSetDevice(D.dev));
-    CU(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
-    {
-        int lo = 0, hi = 0;
-        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CU(cudaStreamCreateWithPriority(&D.stream2, cudaStreamNonBlocking, hi));   // SHA-1 CTAs are dispatched first
-    }
-    for (auto &e : D.ev) CU(cudaEventCreate(&e));
-    CU(cudaEventCreateWithFlags(&D.ev_in, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&D.ev_sha, cudaEventDisableTiming));
+    D.ring.resize(MF_RING);
+    for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
     CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
-    mf_init_tables_kernel<<<2, 256, 0, D.stream>>>();
+    mf_init_tables_kernel<<<2, 256, 0, D.ring[0].stream>>>();
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(D.stream));
+    CU(cudaStreamSynchronize(D.ring[0].stream));
     return MFCAS_OK;
 }
 
 void device_teardown(DeviceState &D) {
     if (D.dev < 0) return;
     cudaSetDevice(D.dev);
-    if (D.stream) cudaStreamSynchronize(D.stream);
-    if (D.stream2) cudaStreamSynchronize(D.stream2);
-    D.in_arena.release(); D.out_arena.release(); D.d_desc.release(); D.d_work.release(); D.slots.release(); D.phase.release();
-    D.h_desc.release(); D.h_res.release();
-    for (auto &e : D.ev) if (e) cudaEventDestroy(e);
-    if (D.ev_in) cudaEventDestroy(D.ev_in);
-    if (D.ev_sha) cudaEventDestroy(D.ev_sha);
-    if (D.stream) cudaStreamDestroy(D.stream);
-    if (D.stream2) cudaStreamDestroy(D.stream2);
+    for (auto &W : D.ring) {
+        if (W.stream) cudaStreamSynchronize(W.stream);
+        if (W.stream2) cudaStreamSynchronize(W.stream2);
+        W.in_arena.release(); W.out_arena.release(); W.d_desc.release(); W.d_work.release(); W.slots.release();
+        W.phase.release(); W.phase2.release(); W.h_desc.release(); W.h_res.release();
+        for (auto &e : W.ev) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_res, W.ev_done}) if (e) cudaEventDestroy(e);
+        if (W.stream) cudaStreamDestroy(W.stream);
+        if (W.stream2) cudaStreamDestroy(W.stream2);
+    }
+    D.ring.clear();
 }
 
-// ------------------------------------------------------------------ device-resident pack
-// want_pack == false: hash only.
-int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                   void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status,
-                   bool want_pack, bool inputs_on_stream) {
-    if (n == 0) return MFCAS_OK;
+static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMING") != nullptr; return on; }
+
+// ------------------------------------------------------------------ pack: enqueue (async) / collect
+// Inputs and outputs are DEVICE pointers.  Everything is enqueued on W's streams, including the copy of the
+// small result block (dst_len, status, digests) to pinned host memory; W.ev_res fires when that is there.
+int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                void *const *d_dst, const uint64_t *dst_cap, bool want_pack) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
-    CU(cudaSetDevice(D.dev));
-    // ---- host-side descriptors
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
         for (uint64_t i = 0; i < n; i++) { n_members += mf_n_members(src_len[i]); n_chunks += mf_n_chunks(src_len[i]); }
@@ -159,14 +184,13 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
     const size_t o_mem = hc.take(sizeof(MfEncMember) * n_members);
     const size_t o_cm = hc.take(sizeof(uint32_t) * n_chunks);
     const size_t desc_bytes = hc.take(0);
-    CU(D.h_desc.ensure(desc_bytes));
-    CU(D.d_desc.ensure(desc_bytes));
-    uint8_t *hd = D.h_desc.as<uint8_t>();
+    CU(W.h_desc.ensure(desc_bytes));
+    CU(W.d_desc.ensure(desc_bytes));
+    uint8_t *hd = W.h_desc.as<uint8_t>();
     MfHashDesc *h_hash = reinterpret_cast<MfHashDesc *>(hd + o_hash);
     MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
     MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
     uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
-    uint32_t mi = 0, ci = 0;
     {   // SHA-1 streams sorted by length (descending): the 32 streams of a CTA then finish together
         std::vector<uint32_t> order(n);
         for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
@@ -179,155 +203,161 @@ int pack_on_device(DeviceState &D, uint32_t flags, uint64_t n, const void *const
             h_hash[k].pad = 0;
         }
     }
-    for (uint64_t i = 0; i < n; i++) {
-        if (!want_pack) continue;
-        h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
-        h_blob[i].dst_cap = dst_cap[i];
-        h_blob[i].first_member = mi;
-        uint64_t nm = mf_n_members(src_len[i]);
-        h_blob[i].n_members = (uint32_t)nm;
-        for (uint64_t m = 0; m < nm; m++) {
-            uint64_t off = m * MF_MEMBER_RAW;
-            uint64_t rl = std::min<uint64_t>(MF_MEMBER_RAW, src_len[i] - off);
-            MfEncMember &M = h_mem[mi];
-            M.src = static_cast<const uint8_t *>(d_src[i]) + off;
-            M.raw_len = (uint32_t)rl;
-            M.n_chunks = (uint32_t)mf_n_chunks(rl);
-            M.first_chunk = ci;
-            M.blob = (uint32_t)i;
-            for (uint32_t k = 0; k < M.n_chunks; k++) h_cm[ci++] = mi;
-            mi++;
+    uint32_t mi = 0, ci = 0;
+    if (want_pack) {
+        for (uint64_t i = 0; i < n; i++) {
+            h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
+            h_blob[i].dst_cap = dst_cap[i];
+            h_blob[i].first_member = mi;
+            uint64_t nm = mf_n_members(src_len[i]);
+            h_blob[i].n_members = (uint32_t)nm;
+            for (uint64_t m = 0; m < nm; m++) {
+                uint64_t off = m * MF_MEMBER_RAW;
+                uint64_t rl = std::min<uint64_t>(MF_MEMBER_RAW, src_len[i] - off);
+                MfEncMember &M = h_mem[mi];
+                M.src = static_cast<const uint8_t *>(d_src[i]) + off;
+                M.raw_len = (uint32_t)rl;
+                M.n_chunks = (uint32_t)mf_n_chunks(rl);
+                M.first_chunk = ci;
+                M.blob = (uint32_t)i;
+                for (uint32_t k = 0; k < M.n_chunks; k++) h_cm[ci++] = mi;
+                mi++;
+            }
         }
     }
-    // ---- device work buffers
     Carver wc;
     const size_t o_comp = wc.take(sizeof(uint32_t) * n_chunks);
     const size_t o_hdr = wc.take(sizeof(uint16_t) * n_chunks);
     const size_t o_seg = wc.take(sizeof(uint16_t) * n_chunks * MF_SEGS_PER_CHUNK);
     const size_t o_crc = wc.take(sizeof(uint32_t) * n_chunks);
     const size_t o_cdst = wc.take(sizeof(uint64_t) * n_chunks);
-    const size_t o_res = wc.take(0);                       // results block, mirrored to the host
+    const size_t o_res = wc.take(0);
     Carver rc;
-    const size_t r_len = rc.take(sizeof(uint64_t) * n, 16);
-    const size_t r_st = rc.take(sizeof(int32_t) * n, 16);
-    const size_t r_sha = rc.take(20 * n, 16);
-    const size_t res_bytes = rc.take(0, 16);
-    CU(D.d_work.ensure(o_res + res_bytes));
-    CU(D.h_res.ensure(res_bytes));
-    if (want_pack) CU(D.slots.ensure((size_t)n_chunks * MF_SLOT + 64));
-    uint8_t *dw = D.d_work.as<uint8_t>();
-    uint8_t *dd = D.d_desc.as<uint8_t>();
+    W.r_len = rc.take(sizeof(uint64_t) * n, 16);
+    W.r_st = rc.take(sizeof(int32_t) * n, 16);
+    W.r_sha = rc.take(20 * n, 16);
+    W.res_bytes = rc.take(0, 16);
+    CU(W.d_work.ensure(o_res + W.res_bytes));
+    CU(W.h_res.ensure(W.res_bytes));
+    if (want_pack) CU(W.slots.ensure((size_t)n_chunks * MF_SLOT + 64));
+    uint8_t *dw = W.d_work.as<uint8_t>();
+    uint8_t *dd = W.d_desc.as<uint8_t>();
     uint8_t *dres = dw + o_res;
-
-    cudaStream_t s = D.stream, s2 = D.stream2;
+    cudaStream_t s = W.stream, s2 = W.stream2;
     unsigned long long *phase = nullptr;      // MFCAS_PHASE_TIMING=1: per-chunk clock64 at phase boundaries
-    static const bool phase_on = getenv("MFCAS_PHASE_TIMING") != nullptr;
-    if (phase_on && want_pack && n_chunks) {
-        CU(D.phase.ensure(n_chunks * 16 * sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(D.phase.p, 0, n_chunks * 16 * sizeof(unsigned long long), D.stream));
-        phase = D.phase.as<unsigned long long>();
+    if (phase_timing_on() && want_pack && n_chunks) {
+        CU(W.phase.ensure(n_chunks * 16 * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(W.phase.p, 0, n_chunks * 16 * sizeof(unsigned long long), s));
+        phase = W.phase.as<unsigned long long>();
     }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(dres + r_st, 0, sizeof(int32_t) * n, s));
-    CU(cudaEventRecord(D.ev_in, s));
-    (void)inputs_on_stream;
-    // ---- SHA-1 on the second stream (serial per blob, so it overlaps the chunk-parallel encoder)
-    CU(cudaStreamWaitEvent(s2, D.ev_in, 0));
-    CU(cudaEventRecord(D.ev[0], s2));
+    CU(cudaMemsetAsync(dres + W.r_st, 0, sizeof(int32_t) * n, s));
+    CU(cudaEventRecord(W.ev_in, s));
+    // ---- SHA-1 on the high-priority second stream (serial per blob: it overlaps the chunk-parallel encoder)
+    CU(cudaStreamWaitEvent(s2, W.ev_in, 0));
+    CU(cudaEventRecord(W.ev[0], s2));
     // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
     // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
     // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
     const unsigned sha_ctas = (unsigned)((n + 31) / 32);
     const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
     unsigned long long *sha_dbg = nullptr;
-    if (phase_on) { CU(D.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = D.phase2.as<unsigned long long>(); }
-    mf_sha1_kernel<<<sha_ctas, 64, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + r_sha, sha_dbg);
+    if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
+    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg);
     CU(cudaGetLastError());
     D.launches++;
-    CU(cudaEventRecord(D.ev[1], s2));
-    CU(cudaEventRecord(D.ev_sha, s2));
+    CU(cudaEventRecord(W.ev[1], s2));
+    CU(cudaEventRecord(W.ev_sha, s2));
     if (want_pack) {
-        CU(cudaEventRecord(D.ev[2], s));
+        CU(cudaEventRecord(W.ev[2], s));
         if (n_chunks) {
             mf_deflate_kernel<<<(unsigned)n_chunks, MF_ENC_THREADS, sizeof(MfEncSmem), s>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
-                D.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
+                W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
                 reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase);
             CU(cudaGetLastError());
             D.launches++;
         }
-        CU(cudaEventRecord(D.ev[3], s));
+        CU(cudaEventRecord(W.ev[3], s));
         mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, s>>>(
             reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
             reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint16_t *>(dw + o_hdr),
             reinterpret_cast<const uint16_t *>(dw + o_seg), reinterpret_cast<const uint32_t *>(dw + o_crc),
-            reinterpret_cast<uint64_t *>(dw + o_cdst), reinterpret_cast<uint64_t *>(dres + r_len), reinterpret_cast<int32_t *>(dres + r_st));
+            reinterpret_cast<uint64_t *>(dw + o_cdst), reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
         CU(cudaGetLastError());
         D.launches++;
         if (n_chunks) {
             mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(
                 reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
-                reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, D.slots.as<uint8_t>(),
+                reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, W.slots.as<uint8_t>(),
                 reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint64_t *>(dw + o_cdst));
             CU(cudaGetLastError());
             D.launches++;
         }
-        CU(cudaEventRecord(D.ev[4], s));
+        CU(cudaEventRecord(W.ev[4], s));
     }
-    CU(cudaStreamWaitEvent(s, D.ev_sha, 0));
-    CU(cudaMemcpyAsync(D.h_res.p, dres, res_bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const uint8_t *hr = D.h_res.as<uint8_t>();
-    if (sha1) memcpy(sha1, hr + r_sha, 20 * n);
-    if (want_pack) {
-        memcpy(dst_len, hr + r_len, sizeof(uint64_t) * n);
-        memcpy(status, hr + r_st, sizeof(int32_t) * n);
-        cudaEventElapsedTime(&D.ms[1], D.ev[2], D.ev[3]);
-        cudaEventElapsedTime(&D.ms[2], D.ev[3], D.ev[4]);
+    CU(cudaStreamWaitEvent(s, W.ev_sha, 0));
+    CU(cudaMemcpyAsync(W.h_res.p, dres, W.res_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(W.ev_res, s));
+    W.n = n; W.n_chunks = n_chunks; W.sha_ctas = sha_ctas; W.timed_pack = want_pack;
+    return MFCAS_OK;
+}
+
+int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+    CU(cudaEventSynchronize(W.ev_res));
+    const uint8_t *hr = W.h_res.as<uint8_t>();
+    const uint64_t n = W.n;
+    if (sha1) memcpy(sha1, hr + W.r_sha, 20 * n);
+    if (W.timed_pack) {
+        memcpy(dst_len, hr + W.r_len, sizeof(uint64_t) * n);
+        memcpy(status, hr + W.r_st, sizeof(int32_t) * n);
+        cudaEventElapsedTime(&D.ms[1], W.ev[2], W.ev[3]);
+        cudaEventElapsedTime(&D.ms[2], W.ev[3], W.ev[4]);
     } else if (status) {
         for (uint64_t i = 0; i < n; i++) status[i] = 0;
     }
-    cudaEventElapsedTime(&D.ms[0], D.ev[0], D.ev[1]);
-    if (sha_dbg) {
-        std::vector<unsigned long long> h((size_t)sha_ctas * 4);
-        CU(cudaMemcpy(h.data(), sha_dbg, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        double a[4] = {0};
-        for (unsigned c = 0; c < sha_ctas; c++) for (int k = 0; k < 4; k++) a[k] += (double)h[c * 4 + k];
-        fprintf(stderr, "[mfcas phase] sha1 over %u CTAs: producer wait=%.0f total=%.0f | consumer wait=%.0f total=%.0f cycles\n", sha_ctas,
-                a[0] / sha_ctas, a[1] / sha_ctas, a[2] / sha_ctas, a[3] / sha_ctas);
-    }
-    if (phase) {
-        std::vector<unsigned long long> h(n_chunks * 16);
-        CU(cudaMemcpy(h.data(), phase, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        // boundaries in program order: 0 start,1 loaded,2 crc done,3 lz done,8 litlen code,9 dist code,10 rle,11 zeroed+sync,12 cl code,13 header,4 ... 7
-        static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
-        static const char *nm[13] = {"load", "crc", "lz77", "litlen_code", "dist_code", "hdr_rle", "zero+sync", "cl_code", "hdr_write", "sync", "bitcount", "pack", "store"};
-        double acc[13] = {0};
-        for (uint64_t c = 0; c < n_chunks; c++)
-            for (int k = 0; k < 13; k++) acc[k] += (double)(h[c * 16 + seq[k + 1]] - h[c * 16 + seq[k]]);
-        fprintf(stderr, "[mfcas phase] deflate, mean cycles per chunk over %llu chunks:", (unsigned long long)n_chunks);
-        for (int k = 0; k < 13; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)n_chunks);
-        fprintf(stderr, "\n");
+    cudaEventElapsedTime(&D.ms[0], W.ev[0], W.ev[1]);
+    if (phase_timing_on()) {
+        if (W.phase2.p) {
+            std::vector<unsigned long long> h((size_t)W.sha_ctas * 4);
+            CU(cudaMemcpy(h.data(), W.phase2.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            double a[4] = {0};
+            for (unsigned c = 0; c < W.sha_ctas; c++) for (int k = 0; k < 4; k++) a[k] += (double)h[c * 4 + k];
+            fprintf(stderr, "[mfcas phase] sha1 over %u CTAs: producer wait=%.0f total=%.0f | consumer wait=%.0f total=%.0f cycles\n", W.sha_ctas,
+                    a[0] / W.sha_ctas, a[1] / W.sha_ctas, a[2] / W.sha_ctas, a[3] / W.sha_ctas);
+        }
+        if (W.timed_pack && W.n_chunks && W.phase.p) {
+            const uint64_t nc = W.n_chunks;
+            std::vector<unsigned long long> h(nc * 16);
+            CU(cudaMemcpy(h.data(), W.phase.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            // boundaries in program order: 0 start,1 loaded,2 crc,3 lz,8 litlen code,9 dist code,10 rle,11 zeroed,12 cl code,13 header,4,5,6,7
+            static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
+            static const char *nm[13] = {"load", "crc", "lz77", "litlen_code", "dist_code", "hdr_rle", "zero+sync", "cl_code", "hdr_write", "sync", "bitcount", "pack", "store"};
+            double acc[13] = {0};
+            for (uint64_t c = 0; c < nc; c++)
+                for (int k = 0; k < 13; k++) acc[k] += (double)(h[c * 16 + seq[k + 1]] - h[c * 16 + seq[k]]);
+            fprintf(stderr, "[mfcas phase] deflate, mean cycles per chunk over %llu chunks:", (unsigned long long)nc);
+            for (int k = 0; k < 13; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)nc);
+            fprintf(stderr, "\n");
+        }
     }
     return MFCAS_OK;
 }
 
-// ------------------------------------------------------------------ device-resident unpack
-int unpack_on_device(DeviceState &D, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                     void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len, int32_t *status) {
-    if (n == 0) return MFCAS_OK;
+// ------------------------------------------------------------------ unpack: enqueue (async) / collect
+int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                  void *const *d_dst, const uint64_t *dst_cap) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
-    CU(cudaSetDevice(D.dev));
     uint64_t max_chunks = 0, max_members = 0;
     for (uint64_t i = 0; i < n; i++) { max_chunks += dst_cap[i] / MF_CHUNK + 1; max_members += dst_cap[i] / MF_MEMBER_RAW + 2; }
     if (max_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
-    CU(D.h_desc.ensure(sizeof(MfDecBlob) * n));
-    MfDecBlob *hb = D.h_desc.as<MfDecBlob>();
+    CU(W.h_desc.ensure(sizeof(MfDecBlob) * n));
+    MfDecBlob *hb = W.h_desc.as<MfDecBlob>();
     for (uint64_t i = 0; i < n; i++) {
         hb[i].src = static_cast<const uint8_t *>(d_src[i]); hb[i].src_len = src_len[i];
         hb[i].dst = static_cast<uint8_t *>(d_dst[i]); hb[i].dst_cap = dst_cap[i];
     }
-    CU(D.d_desc.ensure(sizeof(MfDecBlob) * n));
+    CU(W.d_desc.ensure(sizeof(MfDecBlob) * n));
     Carver wc;
     const size_t o_chunks = wc.take(sizeof(MfDecChunk) * max_chunks);
     const size_t o_members = wc.take(sizeof(MfDecMember) * max_members);
@@ -336,48 +366,53 @@ int unpack_on_device(DeviceState &D, uint64_t n, const void *const *d_src, const
     const size_t o_cnt = wc.take(sizeof(MfDecCounters));
     const size_t o_res = wc.take(0);
     Carver rc;
-    const size_t r_len = rc.take(sizeof(uint64_t) * n, 16);
-    const size_t r_st = rc.take(sizeof(int32_t) * n, 16);
-    const size_t res_bytes = rc.take(0, 16);
-    CU(D.d_work.ensure(o_res + res_bytes));
-    CU(D.h_res.ensure(res_bytes));
-    uint8_t *dw = D.d_work.as<uint8_t>();
+    W.r_len = rc.take(sizeof(uint64_t) * n, 16);
+    W.r_st = rc.take(sizeof(int32_t) * n, 16);
+    W.r_sha = 0;
+    W.res_bytes = rc.take(0, 16);
+    CU(W.d_work.ensure(o_res + W.res_bytes));
+    CU(W.h_res.ensure(W.res_bytes));
+    uint8_t *dw = W.d_work.as<uint8_t>();
     uint8_t *dres = dw + o_res;
-    cudaStream_t s = D.stream;
-    CU(cudaMemcpyAsync(D.d_desc.p, hb, sizeof(MfDecBlob) * n, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + res_bytes) - o_kind, s));     // kind, counters, dst_len, status
-    const MfDecBlob *db = D.d_desc.as<MfDecBlob>();
+    cudaStream_t s = W.stream;
+    CU(cudaMemcpyAsync(W.d_desc.p, hb, sizeof(MfDecBlob) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + W.res_bytes) - o_kind, s));     // kind, counters, dst_len, status
+    const MfDecBlob *db = W.d_desc.as<MfDecBlob>();
     MfDecCounters *cnt = reinterpret_cast<MfDecCounters *>(dw + o_cnt);
-    CU(cudaEventRecord(D.ev[5], s));
+    CU(cudaEventRecord(W.ev[5], s));
     mf_parse_kernel<<<(unsigned)n, 32, 0, s>>>(db, (uint32_t)n, reinterpret_cast<MfDecChunk *>(dw + o_chunks), (uint32_t)max_chunks,
                                                reinterpret_cast<MfDecMember *>(dw + o_members), (uint32_t)max_members, cnt,
-                                               dw + o_kind, reinterpret_cast<uint64_t *>(dres + r_len), reinterpret_cast<int32_t *>(dres + r_st));
+                                               dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
     mf_inflate_chunk_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS - 1) / MF_DEC_WARPS), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
-        reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + r_st));
+        reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
-    CU(cudaEventRecord(D.ev[6], s));
+    CU(cudaEventRecord(W.ev[6], s));
     mf_verify_kernel<<<(unsigned)((max_members * 32 + 127) / 128), 128, 0, s>>>(
-        reinterpret_cast<const MfDecMember *>(dw + o_members), cnt, reinterpret_cast<const uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + r_st));
+        reinterpret_cast<const MfDecMember *>(dw + o_members), cnt, reinterpret_cast<const uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
-    mf_gunzip_lane_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + r_len),
-                                                                  reinterpret_cast<int32_t *>(dres + r_st));
+    mf_gunzip_lane_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len),
+                                                                  reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
     D.launches += 4;
-    CU(cudaEventRecord(D.ev[7], s));
-    CU(cudaMemcpyAsync(D.h_res.p, dres, res_bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    const uint8_t *hr = D.h_res.as<uint8_t>();
-    memcpy(dst_len, hr + r_len, sizeof(uint64_t) * n);
-    memcpy(status, hr + r_st, sizeof(int32_t) * n);
-    cudaEventElapsedTime(&D.ms[3], D.ev[5], D.ev[6]);
-    cudaEventElapsedTime(&D.ms[4], D.ev[6], D.ev[7]);
+    CU(cudaEventRecord(W.ev[7], s));
+    CU(cudaMemcpyAsync(W.h_res.p, dres, W.res_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaEventRecord(W.ev_res, s));
+    W.n = n;
     return MFCAS_OK;
 }
 
-// ------------------------------------------------------------------ host-pointer shards (waves)
-enum class Op { Pack, Hash, Unpack };
+int unpack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, int32_t *status) {
+    CU(cudaEventSynchronize(W.ev_res));
+    const uint8_t *hr = W.h_res.as<uint8_t>();
+    memcpy(dst_len, hr + W.r_len, sizeof(uint64_t) * W.n);
+    memcpy(status, hr + W.r_st, sizeof(int32_t) * W.n);
+    cudaEventElapsedTime(&D.ms[3], W.ev[5], W.ev[6]);
+    cudaEventElapsedTime(&D.ms[4], W.ev[6], W.ev[7]);
+    return MFCAS_OK;
+}
 
+// ------------------------------------------------------------------ host-pointer shards: a ring of waves
 struct Shard {
     std::vector<uint64_t> idx;     // blob indices of this device, in order
 };
@@ -399,67 +434,108 @@ struct CopyPlan {
     }
 };
 
-int run_shard(mfcas_ctx *ctx, DeviceState &D, Op op, const Shard &sh,
-              const void *const *src, const uint64_t *src_len, void *const *dst, const uint64_t *dst_cap,
-              uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
+struct ShardIO {
+    Op op; const Shard *sh;
+    const void *const *src; const uint64_t *src_len; void *const *dst; const uint64_t *dst_cap;
+    uint64_t *dst_len; uint8_t *sha1; int32_t *status;
+};
+
+// stage + enqueue slice [pos, end) of the shard on wave context W
+int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, size_t pos, size_t end,
+                const std::vector<uint64_t> &ioff, const std::vector<uint64_t> &ooff, const std::vector<uint64_t> &caps,
+                uint64_t in_bytes, uint64_t out_bytes) {
+    const size_t wn = end - pos;
+    CU(W.in_arena.ensure(in_bytes + 256));
+    if (io.op != Op::Hash) CU(W.out_arena.ensure(out_bytes + 256));
+    CopyPlan up;
+    W.w_src.resize(wn); W.w_dst.resize(wn); W.w_len.resize(wn); W.w_cap = caps; W.w_ooff = ooff;
+    W.w_dlen.assign(wn, 0); W.w_st.assign(wn, 0); W.w_sha.resize(20 * wn);
+    for (size_t k = 0; k < wn; k++) {
+        uint64_t i = io.sh->idx[pos + k];
+        W.w_src[k] = W.in_arena.as<char>() + ioff[k];
+        W.w_dst[k] = (io.op == Op::Hash) ? nullptr : (void *)(W.out_arena.as<char>() + ooff[k]);
+        W.w_len[k] = io.src_len[i];
+        up.add(io.src[i], (void *)W.w_src[k], io.src_len[i]);
+    }
+    for (auto &it : up.items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, W.stream)); D.h2d += it.n; }
+    int rc;
+    if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data());
+    else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack);
+    if (rc != MFCAS_OK) return rc;
+    W.op = io.op; W.pos = pos; W.wn = wn; W.state = 1;
+    return MFCAS_OK;
+}
+
+// kernels done -> read results, enqueue the output D2H
+int wave_download(DeviceState &D, WaveCtx &W, const ShardIO &io) {
+    int rc = (W.op == Op::Unpack) ? unpack_collect(D, W, W.w_dlen.data(), W.w_st.data())
+                                  : pack_collect(D, W, W.w_dlen.data(), W.w_sha.data(), W.w_st.data());
+    if (rc != MFCAS_OK) return rc;
+    if (W.op != Op::Hash) {
+        CopyPlan down;
+        for (size_t k = 0; k < W.wn; k++) {
+            uint64_t i = io.sh->idx[W.pos + k];
+            io.dst_len[i] = W.w_dlen[k]; io.status[i] = W.w_st[k];
+            if (W.w_st[k] == 0) down.add(io.dst[i], W.w_dst[k], W.w_dlen[k]);
+        }
+        for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, W.stream)); D.d2h += it.n; }
+    } else if (io.status) {
+        for (size_t k = 0; k < W.wn; k++) io.status[io.sh->idx[W.pos + k]] = 0;
+    }
+    if (io.sha1 && W.op != Op::Unpack)
+        for (size_t k = 0; k < W.wn; k++) memcpy(io.sha1 + 20 * io.sh->idx[W.pos + k], W.w_sha.data() + 20 * k, 20);
+    CU(cudaEventRecord(W.ev_done, W.stream));
+    W.state = 2;
+    return MFCAS_OK;
+}
+
+int wave_drain(DeviceState &D, WaveCtx &W, const ShardIO &io) {
+    if (W.state == 1) { int rc = wave_download(D, W, io); if (rc != MFCAS_OK) return rc; }
+    if (W.state == 2) { CU(cudaEventSynchronize(W.ev_done)); W.state = 0; }
+    return MFCAS_OK;
+}
+
+int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
+    const Shard &sh = *io.sh;
     const uint64_t wave_bytes = ctx->wave_bytes;
-    size_t pos = 0;
-    std::vector<const void *> w_src; std::vector<void *> w_dst;
-    std::vector<uint64_t> w_len, w_cap, w_dlen, w_ioff, w_ooff;
-    std::vector<int32_t> w_st; std::vector<uint8_t> w_sha;
     CU(cudaSetDevice(D.dev));
-    while (pos < sh.idx.size()) {
+    size_t pos = 0, w = 0;
+    std::vector<uint64_t> ioff, ooff, caps;
+    int rc = MFCAS_OK;
+    while (pos < sh.idx.size() && rc == MFCAS_OK) {
         // ---- choose the wave: blobs until the staged bytes (in + out) exceed wave_bytes
         size_t end = pos; uint64_t in_bytes = 0, out_bytes = 0;
-        w_ioff.clear(); w_ooff.clear(); w_cap.clear();
+        ioff.clear(); ooff.clear(); caps.clear();
         while (end < sh.idx.size()) {
             uint64_t i = sh.idx[end];
-            uint64_t il = align_up(src_len[i], 256) + 256;
+            uint64_t il = align_up(io.src_len[i], 256) + 256;
             uint64_t oc = 0;
-            if (op == Op::Pack) oc = std::min<uint64_t>(mf_pack_bound(src_len[i]), dst_cap[i]);
-            else if (op == Op::Unpack) oc = dst_cap[i];
+            if (io.op == Op::Pack) oc = std::min<uint64_t>(mf_pack_bound(io.src_len[i]), io.dst_cap[i]);
+            else if (io.op == Op::Unpack) oc = io.dst_cap[i];
             uint64_t ol = align_up(oc, 256) + 256;
             if (end > pos && in_bytes + il + out_bytes + ol > wave_bytes) break;
-            w_ioff.push_back(in_bytes); w_ooff.push_back(out_bytes); w_cap.push_back(oc);
+            ioff.push_back(in_bytes); ooff.push_back(out_bytes); caps.push_back(oc);
             in_bytes += il; out_bytes += ol; end++;
         }
-        const size_t wn = end - pos;
-        CU(D.in_arena.ensure(in_bytes + 256));
-        if (op != Op::Hash) CU(D.out_arena.ensure(out_bytes + 256));
-        // ---- H2D
-        CopyPlan up;
-        w_src.resize(wn); w_dst.resize(wn); w_len.resize(wn); w_dlen.assign(wn, 0); w_st.assign(wn, 0); w_sha.resize(20 * wn);
-        for (size_t k = 0; k < wn; k++) {
-            uint64_t i = sh.idx[pos + k];
-            w_src[k] = D.in_arena.as<char>() + w_ioff[k];
-            w_dst[k] = (op == Op::Hash) ? nullptr : (void *)(D.out_arena.as<char>() + w_ooff[k]);
-            w_len[k] = src_len[i];
-            up.add(src[i], (void *)w_src[k], src_len[i]);
+        WaveCtx &W = D.ring[w % D.ring.size()];
+        rc = wave_drain(D, W, io);                                   // its previous wave (ring full): finish it
+        if (rc == MFCAS_OK) rc = wave_submit(ctx, D, W, io, pos, end, ioff, ooff, caps, in_bytes, out_bytes);
+        // older waves whose kernels have finished: start their output copies now, oldest first
+        for (size_t back = D.ring.size() - 1; back >= 1 && rc == MFCAS_OK; back--) {
+            if (w < back) continue;
+            WaveCtx &O = D.ring[(w - back) % D.ring.size()];
+            if (O.state == 1 && cudaEventQuery(O.ev_res) == cudaSuccess) rc = wave_download(D, O, io);
         }
-        for (auto &it : up.items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, D.stream)); D.h2d += it.n; }
-        // ---- kernels
-        int rc;
-        if (op == Op::Unpack) rc = unpack_on_device(D, wn, w_src.data(), w_len.data(), w_dst.data(), w_cap.data(), w_dlen.data(), w_st.data());
-        else rc = pack_on_device(D, ctx->flags, wn, w_src.data(), w_len.data(), w_dst.data(), w_cap.data(), w_dlen.data(), w_sha.data(), w_st.data(), op == Op::Pack, true);
-        if (rc != MFCAS_OK) return rc;
-        // ---- D2H
-        if (op != Op::Hash) {
-            CopyPlan down;
-            for (size_t k = 0; k < wn; k++) {
-                uint64_t i = sh.idx[pos + k];
-                dst_len[i] = w_dlen[k]; status[i] = w_st[k];
-                if (w_st[k] == 0) down.add(dst[i], w_dst[k], w_dlen[k]);
-            }
-            for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, D.stream)); D.d2h += it.n; }
-            CU(cudaStreamSynchronize(D.stream));
-        } else if (status) {
-            for (size_t k = 0; k < wn; k++) status[sh.idx[pos + k]] = 0;
-        }
-        if (sha1 && op != Op::Unpack)
-            for (size_t k = 0; k < wn; k++) memcpy(sha1 + 20 * sh.idx[pos + k], w_sha.data() + 20 * k, 20);
-        pos = end;
+        (void)cudaGetLastError();
+        pos = end; w++;
     }
-    return MFCAS_OK;
+    // drain in submission order
+    for (size_t k = 0; k < D.ring.size(); k++) {
+        WaveCtx &O = D.ring[(w + k) % D.ring.size()];
+        int r2 = wave_drain(D, O, io);
+        if (rc == MFCAS_OK) rc = r2;
+    }
+    return rc;
 }
 
 int run_batch(mfcas_ctx *ctx, Op op, uint64_t n, const void *const *src, const uint64_t *src_len,
@@ -474,12 +550,15 @@ int run_batch(mfcas_ctx *ctx, Op op, uint64_t n, const void *const *src, const u
     std::vector<Shard> shards(G);
     for (uint64_t i = 0; i < n; i++) shards[i % G].idx.push_back(i);     // round-robin: blob i -> device i mod G
     std::vector<int> rcs(G, MFCAS_OK);
+    auto work = [&](size_t g) {
+        ShardIO io{op, &shards[g], src, src_len, dst, dst_cap, dst_len, sha1, status};
+        rcs[g] = run_shard(ctx, ctx->devs[g], io);
+    };
     if (G == 1) {
-        rcs[0] = run_shard(ctx, ctx->devs[0], op, shards[0], src, src_len, dst, dst_cap, dst_len, sha1, status);
+        work(0);
     } else {
         std::vector<std::thread> th;
-        for (size_t g = 0; g < G; g++)
-            th.emplace_back([&, g] { rcs[g] = run_shard(ctx, ctx->devs[g], op, shards[g], src, src_len, dst, dst_cap, dst_len, sha1, status); });
+        for (size_t g = 0; g < G; g++) th.emplace_back(work, g);
         for (auto &t : th) t.join();
     }
     for (size_t g = 0; g < G; g++)
@@ -587,7 +666,11 @@ int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *cons
     if (n && (!d_src || !src_len || !d_dst || !dst_cap || !dst_len || !sha1 || !status)) return MFCAS_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceState &D = ctx->devs[(size_t)dev_slot];
-    int rc = pack_on_device(D, ctx->flags, n, d_src, src_len, d_dst, dst_cap, dst_len, sha1, status, true, false);
+    if (n == 0) return MFCAS_OK;
+    cudaSetDevice(D.dev);
+    WaveCtx &W = D.ring[0];
+    int rc = pack_submit(D, W, ctx->flags, n, d_src, src_len, d_dst, dst_cap, true);
+    if (rc == MFCAS_OK) rc = pack_collect(D, W, dst_len, sha1, status);
     if (rc != MFCAS_OK) ctx->err = D.err;
     return rc;
 }
@@ -598,14 +681,18 @@ int mfcas_unpack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *co
     if (n && (!d_src || !src_len || !d_dst || !dst_cap || !dst_len || !status)) return MFCAS_E_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceState &D = ctx->devs[(size_t)dev_slot];
-    int rc = unpack_on_device(D, n, d_src, src_len, d_dst, dst_cap, dst_len, status);
+    if (n == 0) return MFCAS_OK;
+    cudaSetDevice(D.dev);
+    WaveCtx &W = D.ring[0];
+    int rc = unpack_submit(D, W, n, d_src, src_len, d_dst, dst_cap);
+    if (rc == MFCAS_OK) rc = unpack_collect(D, W, dst_len, status);
     if (rc != MFCAS_OK) ctx->err = D.err;
     return rc;
 }
 
 void *mfcas_stream(mfcas_ctx *ctx, int dev_slot) {
     if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return nullptr;
-    return (void *)ctx->devs[(size_t)dev_slot].stream;
+    return (void *)ctx->devs[(size_t)dev_slot].ring[0].stream;
 }
 
 void mfcas_counters(mfcas_ctx *ctx, uint64_t *kernel_launches, uint64_t *h2d_bytes, uint64_t *d2h_bytes) {
