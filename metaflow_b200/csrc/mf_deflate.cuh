@@ -124,9 +124,10 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
                   unsigned long long *__restrict__ phase_clk) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfEncSmem &S = *reinterpret_cast<MfEncSmem *>(mf_smem_raw);
-    const uint32_t c = blockIdx.x;
-    if (c >= n_chunks_total) return;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // persistent CTAs: the grid is capped below 2 CTAs x 148 SMs (host side) so that some SMs always keep
+    // a free slot for the latency-critical SHA-1 CTAs of this and the following waves
+    for (uint32_t c = blockIdx.x; c < n_chunks_total; c += gridDim.x) {
     // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
 #define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 16 + (k)] = clock64(); } while (0)
     MF_PHASE(0);
@@ -374,6 +375,8 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
         }
     }
     MF_PHASE(7);
+    __syncthreads();          // shared memory is reused by the next chunk
+    }
 #undef MF_PHASE
 }
 

@@ -7,8 +7,9 @@
 // so everything that is NOT on the chain is moved off the consumer's instruction stream:
 //
 //   CTA = one consumer warp + two producer warps (even / odd blocks), 32 streams (one per lane)
-//   producer: stages 512 bytes per stream with COALESCED 16-byte cp.async (one page per request
-//             instead of 32 -- a lane-per-blob gather thrashes the TLB), byte-swaps, expands
+//   producer: stages 512 bytes per stream with ONE TMA bulk copy per lane (cp.async.bulk + mbarrier
+//             complete_tx; contiguous, one page per request -- a lane-per-blob 16-byte gather thrashes
+//             the TLB and costs 25 instructions per 16 bytes), byte-swaps, expands
 //             the message schedule W[0..79], adds K, and writes (K+W)[t][lane] to shared memory
 //             (also builds the padded tail blocks: 0x80, zeros, 64-bit bit length);
 //   consumer: per round only LDS(K+W) / LOP3(f) / IADD3(T) / LEA.HI(a') / SHF(rol30).
@@ -40,6 +41,7 @@ __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x,
 struct __align__(16) MfShaSmem {
     uint8_t raw[2][2][32][MF_SHA_ROW];    // [producer][group parity][stream][bytes]
     uint32_t kw[2][32][MF_SHA_KWROW];     // [buffer = producer][stream][round]
+    unsigned long long mbar[2][2];        // [producer][group parity]: TMA bulk-copy completion barriers
 };
 
 #define MF_BAR_FULL(b) (1 + (b))
@@ -62,9 +64,30 @@ __device__ __forceinline__ void mf_bar_arrive(int id) {
     }
 }
 
-__device__ __forceinline__ void mf_cp_async16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+// ---- TMA (bulk async copy) + mbarrier helpers: one instruction per lane moves that lane's 512-byte group
+__device__ __forceinline__ uint32_t mf_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mf_mbar_init(void *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mf_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_arrive_tx(void *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_arrive(void *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mf_bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(mf_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(mf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mf_mbar_wait(void *bar, uint32_t parity) {
+    const uint32_t a = mf_smem_u32(bar);
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > (1ll << 31)) __trap();       // ~1 s: never hang the GPU on a protocol bug
+    }
 }
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order
@@ -88,19 +111,32 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
         // ------------------------------------------------------------------ producers (warp 1: even blocks, warp 2: odd blocks)
         const uint32_t pid = warp - 1;
         const uint64_t ngroups = (iters + 7) >> 3;
+        if (lane == 0) { mf_mbar_init(&S.mbar[pid][0], 32); mf_mbar_init(&S.mbar[pid][1], 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        // every lane moves ITS stream's next 512 bytes with one bulk copy (contiguous, one page per request)
         auto issue_group = [&](uint64_t g) {
-            if (g < ngroups) {
-                const uint64_t off = g * MF_SHA_GROUP + lane * 16u;
-                for (int t = 0; t < 32; t++) {
-                    const uint8_t *p = (const uint8_t *)__shfl_sync(0xFFFFFFFFu, (unsigned long long)src, t);
-                    const uint64_t ln = __shfl_sync(0xFFFFFFFFu, (unsigned long long)len, t);
-                    uint32_t nbytes = 0;
-                    if (p && off < ln) nbytes = (ln - off) >= 16 ? 16u : (uint32_t)(ln - off);
-                    if (nbytes) mf_cp_async16(&S.raw[pid][g & 1][t][lane * 16u], p + off, nbytes);
-                    else *reinterpret_cast<uint4 *>(&S.raw[pid][g & 1][t][lane * 16u]) = make_uint4(0, 0, 0, 0);
-                }
+            if (g >= ngroups) return;
+            const uint64_t off = g * MF_SHA_GROUP;
+            uint32_t nbytes = 0;
+            if (src && off < len) { uint64_t rem = len - off; nbytes = rem >= MF_SHA_GROUP ? MF_SHA_GROUP : (uint32_t)((rem + 15) & ~15ull); }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // earlier generic reads/writes of this row come first
+            if (nbytes) { mf_mbar_arrive_tx(&S.mbar[pid][g & 1], nbytes); mf_bulk_g2s(&S.raw[pid][g & 1][lane][0], src + off, nbytes, &S.mbar[pid][g & 1]); }
+            else mf_mbar_arrive(&S.mbar[pid][g & 1]);
+        };
+        auto wait_group = [&](uint64_t g) {
+            mf_mbar_wait(&S.mbar[pid][g & 1], (uint32_t)((g >> 1) & 1));
+            // zero what the copy did not bring: bytes past the end of the message (incl. the <= 15 over-read bytes)
+            const uint64_t off = g * MF_SHA_GROUP;
+            uint32_t have = 0;
+            if (src && off < len) have = (len - off) >= MF_SHA_GROUP ? MF_SHA_GROUP : (uint32_t)(len - off);
+            if (have < MF_SHA_GROUP) {
+                uint8_t *row = &S.raw[pid][g & 1][lane][0];
+                uint32_t k = have;
+                for (; (k & 3u) && k < MF_SHA_GROUP; k++) row[k] = 0;
+                for (; k < MF_SHA_GROUP; k += 4) *reinterpret_cast<uint32_t *>(row + k) = 0;
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
         issue_group(0);
         issue_group(1);
@@ -110,7 +146,7 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
         uint64_t cur_group = ~0ull;
         for (uint64_t i = pid; i < iters; i += 2) {
             const uint64_t g = i >> 3;
-            if (g != cur_group) { asm volatile("cp.async.wait_group 1;" ::: "memory"); __syncwarp(); cur_group = g; }
+            if (g != cur_group) { wait_group(g); cur_group = g; }
             uint32_t w[16];
             {
                 const uint4 *row = reinterpret_cast<const uint4 *>(&S.raw[pid][g & 1][lane][(i & 7) * 64u]);
@@ -146,9 +182,8 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
             // participants (the PTX producer/consumer idiom); a MEMBAR here would drain every store
             mf_bar_arrive(MF_BAR_FULL(b));
             // this producer is done with group g once it has taken its last block of it (blocks 6 or 7)
-            if ((i & 7) >= 6) { __syncwarp(); issue_group(g + 2); }
+            if ((i & 7) >= 6) issue_group(g + 2);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (dbg && lane == 0 && pid == 0) { dbg[blockIdx.x * 4 + 0] = (unsigned long long)pwait; dbg[blockIdx.x * 4 + 1] = (unsigned long long)(clock64() - pstart); }
     } else {
         // ------------------------------------------------------------------ consumer

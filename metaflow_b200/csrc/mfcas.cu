@@ -66,7 +66,7 @@ enum class Op { Pack, Hash, Unpack };
 struct WaveCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_res = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_cmp = nullptr, ev_res = nullptr, ev_done = nullptr;
     DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2;
     HostBuf h_desc, h_res;
     // bookkeeping of the submitted wave
@@ -84,6 +84,7 @@ struct WaveCtx {
 
 struct DeviceState {
     int dev = -1;
+    cudaStream_t compute = nullptr;      // all chunk-parallel encode kernels of all waves, in submission order
     std::vector<WaveCtx> ring;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -123,6 +124,8 @@ struct Carver {
 };
 
 #define MF_RING 8
+// encoder CTAs resident at once: 2 per SM x 148 SMs minus 24, i.e. ~24 SMs keep one free 100+ KB slot for SHA-1 CTAs
+#define MF_ENC_GRID_CAP 272u
 
 int wave_setup(DeviceState &D, WaveCtx &W) {
     int lo = 0, hi = 0;
@@ -132,6 +135,7 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
     for (auto &e : W.ev) CU(cudaEventCreate(&e));
     CU(cudaEventCreateWithFlags(&W.ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_sha, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&W.ev_cmp, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_res, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
     return MFCAS_OK;
@@ -139,6 +143,7 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
 
 int device_setup(DeviceState &D) {
     CU(cudaSetDevice(D.dev));
+    CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
     CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -159,11 +164,12 @@ void device_teardown(DeviceState &D) {
         W.in_arena.release(); W.out_arena.release(); W.d_desc.release(); W.d_work.release(); W.slots.release();
         W.phase.release(); W.phase2.release(); W.h_desc.release(); W.h_res.release();
         for (auto &e : W.ev) if (e) cudaEventDestroy(e);
-        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_res, W.ev_done}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_done}) if (e) cudaEventDestroy(e);
         if (W.stream) cudaStreamDestroy(W.stream);
         if (W.stream2) cudaStreamDestroy(W.stream2);
     }
     D.ring.clear();
+    if (D.compute) { cudaStreamSynchronize(D.compute); cudaStreamDestroy(D.compute); D.compute = nullptr; }
 }
 
 static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMING") != nullptr; return on; }
@@ -269,17 +275,19 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     CU(cudaEventRecord(W.ev[1], s2));
     CU(cudaEventRecord(W.ev_sha, s2));
     if (want_pack) {
-        CU(cudaEventRecord(W.ev[2], s));
+        cudaStream_t sc = D.compute;          // one encoder kernel at a time per device (see MF_ENC_GRID_CAP)
+        CU(cudaStreamWaitEvent(sc, W.ev_in, 0));
+        CU(cudaEventRecord(W.ev[2], sc));
         if (n_chunks) {
-            mf_deflate_kernel<<<(unsigned)n_chunks, MF_ENC_THREADS, sizeof(MfEncSmem), s>>>(
+            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, MF_ENC_GRID_CAP), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
                 reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase);
             CU(cudaGetLastError());
             D.launches++;
         }
-        CU(cudaEventRecord(W.ev[3], s));
-        mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, s>>>(
+        CU(cudaEventRecord(W.ev[3], sc));
+        mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, sc>>>(
             reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
             reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint16_t *>(dw + o_hdr),
             reinterpret_cast<const uint16_t *>(dw + o_seg), reinterpret_cast<const uint32_t *>(dw + o_crc),
@@ -287,14 +295,16 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         CU(cudaGetLastError());
         D.launches++;
         if (n_chunks) {
-            mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, s>>>(
+            mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, sc>>>(
                 reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
                 reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, W.slots.as<uint8_t>(),
                 reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint64_t *>(dw + o_cdst));
             CU(cudaGetLastError());
             D.launches++;
         }
-        CU(cudaEventRecord(W.ev[4], s));
+        CU(cudaEventRecord(W.ev[4], sc));
+        CU(cudaEventRecord(W.ev_cmp, sc));
+        CU(cudaStreamWaitEvent(s, W.ev_cmp, 0));
     }
     CU(cudaStreamWaitEvent(s, W.ev_sha, 0));
     CU(cudaMemcpyAsync(W.h_res.p, dres, W.res_bytes, cudaMemcpyDeviceToHost, s));
