@@ -11,7 +11,8 @@
 //   pass 1  CRC-32 of the chunk (64-byte piece per lane, slice-by-4 tables in smem, GF(2) combine)
 //   pass 2  LZ77: each warp walks its 1 KiB segments 32 positions at a time (hash probe + in-window
 //           probes via warp shuffles, cooperative match extension, ballot-ordered greedy parse)
-//   pass 3  CTA-parallel Huffman construction (bitonic sort, two-queue merge, Kraft repair)
+//   pass 3  prefix codes by Kraft-slack refinement, warp-synchronous in registers (warp 0 literal/length,
+//           warp 1 distance), then the dynamic-block header with position-parallel run-length tokens
 //   pass 4  per-lane bit counting, warp-shuffle prefix scans -> every token's bit offset
 //   pass 5  bit packing into smem, then coalesced 16-byte stores smem -> HBM slot
 // HBM traffic per chunk: raw bytes read once, packed bytes written once (+ the gather copy).
@@ -88,6 +89,301 @@ __device__ __forceinline__ uint32_t mf_crc_words(const uint8_t *s, uint32_t off,
     return crc;
 }
 
+// ------------------------------------------------------------------ warp-synchronous code construction
+// One warp builds a complete prefix code for up to 32*K symbols entirely in registers + a few shared
+// counters: symbol s = k*32 + lane.  Same Kraft-slack refinement as mf_huff_build (mf_core.h) but with the
+// greedy order replaced by 256 benefit/cost buckets (one scan per round instead of a sort) and an exact
+// completion step, so no loop is longer than K and nothing waits on a CTA barrier.
+struct MfWarpCodeScratch {
+    uint32_t bcost[256];     // code space wanted per benefit/cost bucket
+    uint32_t lcnt[16];       // codes per length
+    uint32_t nxt[16];        // next canonical code per length
+};
+
+__device__ __forceinline__ uint32_t mf_warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+    return v;
+}
+__device__ __forceinline__ uint32_t mf_warp_min(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, d));
+    return v;
+}
+
+template <int K>
+__device__ __forceinline__ void mf_build_code_warp(const uint32_t *hist, int n, int maxbits, uint8_t *lens, uint32_t *codes,
+                                                   MfWarpCodeScratch &W, uint32_t lane) {
+    uint32_t f[K], l[K];
+    uint32_t used = 0, T = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) { int s = k * 32 + (int)lane; f[k] = s < n ? hist[s] : 0u; used += f[k] != 0; T += f[k]; }
+    used = mf_warp_sum(used);
+    if (used < 2) {                       // zlib forces at least two codes; so do we (symbols 0, 1, ...)
+        uint32_t need = 2 - used;
+        uint32_t z = __ballot_sync(0xFFFFFFFFu, f[0] == 0);
+        uint32_t rank = __popc(z & ((1u << lane) - 1u));
+        if (f[0] == 0 && rank < need) { f[0] = 1; T += 1; }
+    }
+    T = mf_warp_sum(T);
+    const uint32_t full = 1u << maxbits;
+    uint32_t mass = 0;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        uint32_t lk = 0;
+        if (f[k]) {
+            int a = 31 - __clz((int)T), b = 31 - __clz((int)f[k]);
+            lk = (uint32_t)(a - b);
+            if ((f[k] << lk) < T) lk++;               // smallest l with f * 2^l >= T  (Shannon length)
+            lk = min(max(lk, 1u), (uint32_t)maxbits);
+            mass += full >> lk;
+        }
+        l[k] = lk;
+    }
+    mass = mf_warp_sum(mass);
+    while (mass > full) {                 // clamping to maxbits over-subscribed the code space: lengthen the rarest
+        uint32_t best = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < K; k++) if (l[k] && l[k] < (uint32_t)maxbits) best = min(best, (f[k] << 9) | (uint32_t)(k * 32 + (int)lane));
+        best = mf_warp_min(best);
+        if (best == 0xFFFFFFFFu) break;
+        const uint32_t bs = best & 511u;
+        uint32_t newl = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) if ((uint32_t)(k * 32 + (int)lane) == bs) { l[k]++; newl = l[k]; }
+        newl = __shfl_sync(0xFFFFFFFFu, newl, bs & 31u);
+        mass -= full >> newl;
+    }
+    uint32_t slack = full - mass;
+    const float inv_t = 256.0f / (float)T;
+    for (int round = 0; round < 3 && slack; round++) {
+        for (uint32_t i = lane; i < 256; i += 32) W.bcost[i] = 0;
+        __syncwarp();
+        uint32_t bk[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            bk[k] = 0xFFFFFFFFu;
+            if (l[k] > 1) {
+                uint32_t key = f[k] << l[k];                     // in [T, 2T) unless the length was clamped
+                uint32_t b = key > T ? min(255u, (uint32_t)((float)(key - T) * inv_t)) : 0u;
+                bk[k] = b;
+                atomicAdd(&W.bcost[b], full >> l[k]);
+            }
+        }
+        __syncwarp();
+        // lane j owns buckets 255-8j .. 248-8j (descending benefit); accept the longest prefix that fits
+        uint32_t c[8], lsum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { c[j] = W.bcost[255 - 8 * (int)lane - j]; lsum += c[j]; }
+        uint32_t incl = lsum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += u; }
+        uint32_t cum = incl - lsum, thr_local = 0;
+        bool rejected = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (!rejected) {
+                if (cum + c[j] <= slack) cum += c[j];
+                else { rejected = true; thr_local = 256u - 8u * lane - (uint32_t)j; }   // first rejected bucket + 1
+            }
+        }
+        const uint32_t rej = __ballot_sync(0xFFFFFFFFu, rejected);
+        uint32_t thr = 0, consumed;
+        if (rej) {
+            const int L = __ffs(rej) - 1;
+            thr = __shfl_sync(0xFFFFFFFFu, thr_local, L);
+            consumed = __shfl_sync(0xFFFFFFFFu, cum, L);
+        } else {
+            consumed = __shfl_sync(0xFFFFFFFFu, cum, 31);
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) if (bk[k] != 0xFFFFFFFFu && bk[k] >= thr) l[k]--;
+        if (consumed == 0) break;
+        slack -= consumed;
+        __syncwarp();
+    }
+    // exact completion: DEFLATE decoders reject an under-full code, the Kraft sum must end at exactly 1
+    if (lane < 16) W.lcnt[lane] = 0;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) if (l[k]) atomicAdd(&W.lcnt[l[k]], 1u);
+    __syncwarp();
+    for (int guard = 0; slack && guard < 64; guard++) {
+        const uint32_t myc = (lane >= 2 && (int)lane <= maxbits) ? W.lcnt[lane] : 0u;
+        const uint32_t ok = __ballot_sync(0xFFFFFFFFu, myc > 0 && (full >> lane) <= slack);
+        if (!ok) break;
+        const uint32_t L = (uint32_t)__ffs(ok) - 1u;      // shortest such length = largest piece of code space
+        const uint32_t cst = full >> L;
+        const uint32_t cntL = __shfl_sync(0xFFFFFFFFu, myc, (int)L);
+        const uint32_t take = min(cntL, slack / cst);
+        uint32_t done = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const bool cand = l[k] == L;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, cand);
+            const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+            if (cand && done + rank < take) l[k]--;
+            done += __popc(m);
+        }
+        __syncwarp();
+        if (lane == 0) { W.lcnt[L] -= take; W.lcnt[L - 1] += take; }
+        slack -= take * cst;
+        __syncwarp();
+    }
+    // canonical codes (RFC 1951 3.2.2): first code per length, then rank among equal lengths in symbol order
+    if (lane == 0) {
+        uint32_t code = 0;
+        W.nxt[0] = 0;
+        for (int b = 1; b <= 15; b++) { code = (code + (b - 1 >= 1 ? W.lcnt[b - 1] : 0u)) << 1; W.nxt[b] = code; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const uint32_t L = l[k];
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, L);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t code = L ? W.nxt[L] + rank : 0u;
+        __syncwarp();
+        if (L && rank == 0) W.nxt[L] += __popc(peers);
+        __syncwarp();
+        const int s = k * 32 + (int)lane;
+        if (s < n) { lens[s] = (uint8_t)L; codes[s] = L ? ((L << 16) | (__brev(code) >> (32 - L))) : 0u; }
+    }
+    __syncwarp();
+}
+
+// Warp-synchronous dynamic-block header (RFC 1951 3.2.7): every position of the code-length sequence decides
+// locally which run-length token (if any) starts there, the code-length code is built from the token
+// histogram, and the tokens are placed with a prefix scan of their bit lengths.  out = zeroed words.
+struct MfWarpHdrScratch {
+    MfWarpCodeScratch code;
+    uint32_t clhist[32];
+    uint32_t clcodes[32];
+    uint8_t cllens[32];
+    uint8_t seq[320];
+};
+
+__device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const uint8_t *d_lens, uint32_t *out, MfWarpHdrScratch &H, uint32_t lane) {
+    // HLIT / HDIST: trim trailing zero lengths
+    int hlit = 257, hdist = 1;
+    for (int k = 8; k >= 0; k--) {
+        int s = k * 32 + (int)lane;
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, s < 286 && ll_lens[s] != 0);
+        if (m) { hlit = max(257, k * 32 + (32 - __clz((int)m))); break; }
+    }
+    {
+        uint32_t m = __ballot_sync(0xFFFFFFFFu, lane < 30 && d_lens[lane] != 0);
+        if (m) hdist = max(1, 32 - __clz((int)m));
+    }
+    const int n = hlit + hdist;
+    for (int p = (int)lane; p < n; p += 32) H.seq[p] = p < hlit ? ll_lens[p] : d_lens[p - hlit];
+    if (lane < 32) H.clhist[lane] = 0;
+    __syncwarp();
+    // run start a(p) (forward max-scan of start positions) and run end e(p) (backward min-scan), rows k = p / 32
+    uint32_t v[10], a[10], e[10];
+    uint32_t carry_v = 0xFFFFu, carry_a = 0;
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        const int p = k * 32 + (int)lane;
+        v[k] = p < n ? H.seq[p] : (0x100u + (uint32_t)(p & 1));          // sentinels never form runs with data
+        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v[k], 1);
+        if (lane == 0) prev = carry_v;
+        uint32_t st = (v[k] != prev) ? (uint32_t)p : 0u;
+        if (lane == 0 && st == 0) st = carry_a;                           // run continues from the previous row
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, st, d); if ((int)lane >= d) st = max(st, u); }
+        a[k] = st;
+        carry_v = __shfl_sync(0xFFFFFFFFu, v[k], 31);
+        carry_a = __shfl_sync(0xFFFFFFFFu, st, 31);
+    }
+    uint32_t carry_e = 320u, carry_nv = 0xFFFFu;
+#pragma unroll
+    for (int k = 9; k >= 0; k--) {
+        const int p = k * 32 + (int)lane;
+        uint32_t nxtv = __shfl_down_sync(0xFFFFFFFFu, v[k], 1);
+        if (lane == 31) nxtv = carry_nv;
+        uint32_t en = (v[k] != nxtv) ? (uint32_t)(p + 1) : 0xFFFFu;       // run ends right after p
+        if (lane == 31 && en == 0xFFFFu) en = carry_e;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_down_sync(0xFFFFFFFFu, en, d); if ((int)lane + d < 32) en = min(en, u); }
+        e[k] = en;
+        carry_nv = __shfl_sync(0xFFFFFFFFu, v[k], 0);
+        carry_e = __shfl_sync(0xFFFFFFFFu, en, 0);
+    }
+    // token decision per position
+    uint32_t tsym[10], text[10];          // tsym 0xFF = no token here
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        const int p = k * 32 + (int)lane;
+        uint32_t sym = 0xFFu, ext = 0;
+        if (p < n) {
+            const uint32_t R = e[k] - a[k], off = (uint32_t)p - a[k], val = v[k];
+            if (val == 0) {
+                const uint32_t fullr = R / 138u, rem = R - fullr * 138u;
+                if (off < fullr * 138u) { if (off % 138u == 0) { sym = 18; ext = 127; } }
+                else {
+                    const uint32_t ro = off - fullr * 138u;
+                    if (rem >= 11) { if (ro == 0) { sym = 18; ext = rem - 11; } }
+                    else if (rem >= 3) { if (ro == 0) { sym = 17; ext = rem - 3; } }
+                    else sym = 0;
+                }
+            } else if (off == 0) sym = val;
+            else {
+                const uint32_t rest = R - 1, o = off - 1, fullg = rest / 6u, rem = rest - fullg * 6u;
+                if (o < fullg * 6u) { if (o % 6u == 0) { sym = 16; ext = 3; } }
+                else {
+                    const uint32_t ro = o - fullg * 6u;
+                    if (rem >= 3) { if (ro == 0) { sym = 16; ext = rem - 3; } }
+                    else sym = val;
+                }
+            }
+            if (sym != 0xFFu) atomicAdd(&H.clhist[sym], 1u);
+        }
+        tsym[k] = sym; text[k] = ext;
+    }
+    __syncwarp();
+    mf_build_code_warp<1>(H.clhist, 19, 7, H.cllens, H.clcodes, H.code, lane);
+    // HCLEN
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint32_t ord = 0;
+#pragma unroll
+    for (int i = 0; i < 19; i++) if ((int)lane == i) ord = order[i];
+    const uint32_t nz = __ballot_sync(0xFFFFFFFFu, lane < 19 && H.cllens[ord] != 0);
+    const int hclen = max(4, 32 - __clz((int)nz));
+    // fixed part: BFINAL=0, BTYPE=10, HLIT, HDIST, HCLEN, then HCLEN x 3 bits
+    if (lane == 0) {
+        uint32_t w0 = 0u | (2u << 1) | ((uint32_t)(hlit - 257) << 3) | ((uint32_t)(hdist - 1) << 8) | ((uint32_t)(hclen - 4) << 13);
+        atomicOr(&out[0], w0);
+    }
+    if ((int)lane < hclen) {
+        const uint32_t bit = 17u + 3u * lane, val = H.cllens[ord];
+        atomicOr(&out[bit >> 5], val << (bit & 31u));
+        if ((bit & 31u) > 29u) atomicOr(&out[(bit >> 5) + 1], val >> (32u - (bit & 31u)));
+    }
+    // tokens: prefix scan of bit lengths in position order
+    uint32_t base = 17u + 3u * (uint32_t)hclen;
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        uint32_t bits = 0, word = 0;
+        if (tsym[k] != 0xFFu) {
+            const uint32_t ce = H.clcodes[tsym[k]];
+            const uint32_t cl = ce >> 16, eb = tsym[k] == 16 ? 2u : (tsym[k] == 17 ? 3u : (tsym[k] == 18 ? 7u : 0u));
+            word = (ce & 0xFFFFu) | (text[k] << cl);
+            bits = cl + eb;
+        }
+        uint32_t incl = bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += u; }
+        if (bits) {
+            const uint32_t bit = base + incl - bits;
+            atomicOr(&out[bit >> 5], word << (bit & 31u));
+            if ((bit & 31u) + bits > 32u) atomicOr(&out[(bit >> 5) + 1], word >> (32u - (bit & 31u)));
+        }
+        base += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    return base;      // header length in bits
+}
+
 #define MF_ENC_THREADS 512
 #define MF_ENC_WARPS 16
 #define MF_HASH_BITS 10
@@ -104,8 +400,9 @@ struct __align__(16) MfEncSmem {
     uint32_t d_codes[32];
     uint8_t ll_lens[288];
     uint8_t d_lens[32];
-    MfHuffScratch huff;
-    MfHdrScratch hdr;
+    MfWarpHdrScratch whdr;           // warp 0: litlen code, then the block header
+    MfWarpCodeScratch wdist;         // warp 1: distance code
+    uint32_t hdr_bits;
     uint32_t nmatch[MF_SEGS_PER_CHUNK];
     uint32_t seg_bits[MF_SEGS_PER_CHUNK];
     uint32_t seg_off[MF_SEGS_PER_CHUNK];
@@ -264,22 +561,25 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
 
     MF_PHASE(3);
     // ---- pass 3: Huffman codes, block header
-    mf_huff_build<512>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.huff);
-    MF_PHASE(8);
-    mf_huff_build<32>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.huff);
-    MF_PHASE(9);
-    if (tid == 0) mf_hdr_rle(S.ll_lens, S.d_lens, S.hdr);
-    MF_PHASE(10);
-    {   // region B is dead as hash tables now: zero it for the bit writers
+    // warp 0: literal/length code; warp 1: distance code; everyone else zeroes region B (dead as hash tables
+    // now) for the bit writers.  No CTA barrier inside, and no loop longer than 10 iterations.
+    if (warp == 0) mf_build_code_warp<9>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.whdr.code, lane);
+    else if (warp == 1) mf_build_code_warp<1>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.wdist, lane);
+    else {
         uint4 *z = reinterpret_cast<uint4 *>(S.regionB);
-        for (uint32_t i = tid; i < MF_REGION_B / 16; i += MF_ENC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        for (uint32_t i = tid - 64; i < MF_REGION_B / 16; i += MF_ENC_THREADS - 64) z[i] = make_uint4(0, 0, 0, 0);
     }
+    MF_PHASE(8);
     __syncthreads();
-    MF_PHASE(11);
-    mf_huff_build<32>(S.hdr.clhist, 19, 7, S.hdr.cllens, S.hdr.clcodes, S.huff);
-    MF_PHASE(12);
+    MF_PHASE(9);
     uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
-    if (tid == 0) mf_hdr_write(outw, S.hdr);
+    if (warp == 0) {
+        uint32_t hb = mf_header_warp(S.ll_lens, S.d_lens, outw, S.whdr, lane);
+        if (lane == 0) S.hdr_bits = hb;
+    }
+    MF_PHASE(10);
+    MF_PHASE(11);
+    MF_PHASE(12);
     MF_PHASE(13);
     __syncthreads();
 
@@ -301,10 +601,10 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     if (warp == 0) {
         uint32_t b = S.seg_bits[lane];
         uint32_t incl = mf_warp_incl_scan(b, lane);
-        S.seg_off[lane] = S.hdr.hdr_bits + incl - b;
+        S.seg_off[lane] = S.hdr_bits + incl - b;
         if (lane == 31) {
             uint32_t eob = S.ll_codes[256];
-            uint32_t end_tokens = S.hdr.hdr_bits + incl;            // where EOB goes
+            uint32_t end_tokens = S.hdr_bits + incl;            // where EOB goes
             uint32_t end_bits = end_tokens + (eob >> 16) + 3u;       // + empty stored block header (000)
             uint32_t dyn_bytes = ((end_bits + 7u) >> 3) + 4u;        // + LEN/NLEN of the sync marker
             S.total_bits = end_tokens;
@@ -368,7 +668,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
         if (tid < MF_SEGS_PER_CHUNK) seg_bits_out[(size_t)c * MF_SEGS_PER_CHUNK + tid] = S.stored ? 0 : (uint16_t)S.seg_bits[tid];
         if (tid == 0) {
             comp_bytes_out[c] = cb;
-            hdr_bits_out[c] = S.stored ? (uint16_t)MF_STORED_MARK : (uint16_t)S.hdr.hdr_bits;
+            hdr_bits_out[c] = S.stored ? (uint16_t)MF_STORED_MARK : (uint16_t)S.hdr_bits;
             uint32_t crc = 0;
             for (int k = 0; k < MF_ENC_WARPS; k++) crc ^= S.crc_part[k];
             chunk_crc_out[c] = crc;

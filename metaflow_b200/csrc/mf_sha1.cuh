@@ -92,7 +92,7 @@ __device__ __forceinline__ void mf_mbar_wait(void *bar, uint32_t parity) {
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order
 __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
-                                                      unsigned long long *__restrict__ dbg) {
+                                                      unsigned long long *__restrict__ dbg, uint32_t one_arg) {
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -189,17 +189,21 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
         // ------------------------------------------------------------------ consumer
         uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
         long long cwait = 0, cstart = dbg ? clock64() : 0;
+        const uint32_t one = one_arg;      // == 1, but only the host knows
         for (uint64_t i = 0; i < iters; i++) {
             const int bsel = (int)(i & 1);
             { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_FULL(bsel)); if (dbg) cwait += clock64() - t0_; }
             const uint4 *kwv = reinterpret_cast<const uint4 *>(&S.kw[bsel][lane][0]);
             uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
+            // The integer ALU pipe issues one warp instruction per 2 cycles per SM sub-partition, and a round
+            // needs LOP3 + LEA.HI + SHF there already; the two additions that build T go to the FMA pipe as
+            // IMAD with an opaque multiplier of 1 (ptxas would otherwise fold them back into an ALU IADD3).
             // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI).
             // The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the
             // rotate-add and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
 #define MF_RND(F, a, b, c, d, e, kw_) { uint32_t f_ = F(b, c, d); \
-        asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
-            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
+        asm("{\n\t.reg .u32 t_, r_;\n\tmad.lo.u32 t_, %1, %5, %2;\n\tmad.lo.u32 t_, %3, %5, t_;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
+            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a), "r"(one)); \
         b = mf_rol(b, 30); }
 #define MF_RND20(F, q) { \
         uint4 k0 = kwv[5 * (q)], k1 = kwv[5 * (q) + 1], k2 = kwv[5 * (q) + 2], k3 = kwv[5 * (q) + 3], k4 = kwv[5 * (q) + 4]; \

@@ -123,7 +123,7 @@ struct Carver {
     size_t take(size_t bytes, size_t align = 256) { off = align_up(off, align); size_t o = off; off += bytes; return o; }
 };
 
-#define MF_RING 8
+#define MF_RING 12
 // encoder CTAs resident at once: 2 per SM x 148 SMs minus 24, i.e. ~24 SMs keep one free 100+ KB slot for SHA-1 CTAs
 #define MF_ENC_GRID_CAP 272u
 
@@ -269,7 +269,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
     unsigned long long *sha_dbg = nullptr;
     if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
-    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg);
+    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, 1u);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(W.ev[1], s2));
@@ -342,7 +342,7 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
             CU(cudaMemcpy(h.data(), W.phase.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             // boundaries in program order: 0 start,1 loaded,2 crc,3 lz,8 litlen code,9 dist code,10 rle,11 zeroed,12 cl code,13 header,4,5,6,7
             static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
-            static const char *nm[13] = {"load", "crc", "lz77", "litlen_code", "dist_code", "hdr_rle", "zero+sync", "cl_code", "hdr_write", "sync", "bitcount", "pack", "store"};
+            static const char *nm[13] = {"load", "crc", "lz77", "codes(warp0)", "codes_sync", "header", "-", "-", "-", "sync", "bitcount", "pack", "store"};
             double acc[13] = {0};
             for (uint64_t c = 0; c < nc; c++)
                 for (int k = 0; k < 13; k++) acc[k] += (double)(h[c * 16 + seq[k + 1]] - h[c * 16 + seq[k]]);
@@ -472,36 +472,41 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
     if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data());
     else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack);
     if (rc != MFCAS_OK) return rc;
+    // Output copies are enqueued right behind the kernels, without a host round trip: the whole destination
+    // slot (its capacity) is copied -- for packed output a few per cent more than the bytes produced, for decoded
+    // output exactly the decoded size -- so that D2H of this wave overlaps H2D and kernels of the next ones.
+    if (io.op != Op::Hash) {
+        CopyPlan down;
+        for (size_t k = 0; k < wn; k++) down.add(io.dst[io.sh->idx[pos + k]], W.w_dst[k], W.w_cap[k]);
+        for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, W.stream)); D.d2h += it.n; }
+    }
+    CU(cudaEventRecord(W.ev_done, W.stream));
     W.op = io.op; W.pos = pos; W.wn = wn; W.state = 1;
     return MFCAS_OK;
 }
 
-// kernels done -> read results, enqueue the output D2H
-int wave_download(DeviceState &D, WaveCtx &W, const ShardIO &io) {
+// everything of the wave is done -> hand the per-blob results to the caller
+int wave_finish(DeviceState &D, WaveCtx &W, const ShardIO &io) {
     int rc = (W.op == Op::Unpack) ? unpack_collect(D, W, W.w_dlen.data(), W.w_st.data())
                                   : pack_collect(D, W, W.w_dlen.data(), W.w_sha.data(), W.w_st.data());
     if (rc != MFCAS_OK) return rc;
+    CU(cudaEventSynchronize(W.ev_done));
     if (W.op != Op::Hash) {
-        CopyPlan down;
         for (size_t k = 0; k < W.wn; k++) {
             uint64_t i = io.sh->idx[W.pos + k];
             io.dst_len[i] = W.w_dlen[k]; io.status[i] = W.w_st[k];
-            if (W.w_st[k] == 0) down.add(io.dst[i], W.w_dst[k], W.w_dlen[k]);
         }
-        for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, W.stream)); D.d2h += it.n; }
     } else if (io.status) {
         for (size_t k = 0; k < W.wn; k++) io.status[io.sh->idx[W.pos + k]] = 0;
     }
     if (io.sha1 && W.op != Op::Unpack)
         for (size_t k = 0; k < W.wn; k++) memcpy(io.sha1 + 20 * io.sh->idx[W.pos + k], W.w_sha.data() + 20 * k, 20);
-    CU(cudaEventRecord(W.ev_done, W.stream));
-    W.state = 2;
+    W.state = 0;
     return MFCAS_OK;
 }
 
 int wave_drain(DeviceState &D, WaveCtx &W, const ShardIO &io) {
-    if (W.state == 1) { int rc = wave_download(D, W, io); if (rc != MFCAS_OK) return rc; }
-    if (W.state == 2) { CU(cudaEventSynchronize(W.ev_done)); W.state = 0; }
+    if (W.state == 1) return wave_finish(D, W, io);
     return MFCAS_OK;
 }
 
@@ -530,12 +535,6 @@ int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
         WaveCtx &W = D.ring[w % D.ring.size()];
         rc = wave_drain(D, W, io);                                   // its previous wave (ring full): finish it
         if (rc == MFCAS_OK) rc = wave_submit(ctx, D, W, io, pos, end, ioff, ooff, caps, in_bytes, out_bytes);
-        // older waves whose kernels have finished: start their output copies now, oldest first
-        for (size_t back = D.ring.size() - 1; back >= 1 && rc == MFCAS_OK; back--) {
-            if (w < back) continue;
-            WaveCtx &O = D.ring[(w - back) % D.ring.size()];
-            if (O.state == 1 && cudaEventQuery(O.ev_res) == cudaSuccess) rc = wave_download(D, O, io);
-        }
         (void)cudaGetLastError();
         pos = end; w++;
     }
