@@ -64,6 +64,7 @@ def load():
             "%s is missing: build it with `make -C metaflow_b200/csrc` (nvcc, sm_100a). "
             "The artifact hot path has no CPU fallback." % LIB_PATH
         )
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # see mfcas_create: one work queue per wave stream
     try:
         lib = ctypes.CDLL(LIB_PATH)
     except OSError as e:

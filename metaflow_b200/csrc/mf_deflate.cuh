@@ -263,7 +263,8 @@ struct MfWarpHdrScratch {
     uint8_t seq[320];
 };
 
-__device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const uint8_t *d_lens, uint32_t *out, MfWarpHdrScratch &H, uint32_t lane) {
+__device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const uint8_t *d_lens, uint32_t *out, MfWarpHdrScratch &H, uint32_t lane,
+                                                   unsigned long long *ph) {
     // HLIT / HDIST: trim trailing zero lengths
     int hlit = 257, hdist = 1;
     for (int k = 8; k >= 0; k--) {
@@ -279,6 +280,7 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
     for (int p = (int)lane; p < n; p += 32) H.seq[p] = p < hlit ? ll_lens[p] : d_lens[p - hlit];
     if (lane < 32) H.clhist[lane] = 0;
     __syncwarp();
+    if (ph && lane == 0) ph[4] = clock64();
     // run start a(p) (forward max-scan of start positions) and run end e(p) (backward min-scan), rows k = p / 32
     uint32_t v[10], a[10], e[10];
     uint32_t carry_v = 0xFFFFu, carry_a = 0;
@@ -296,6 +298,7 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
         carry_v = __shfl_sync(0xFFFFFFFFu, v[k], 31);
         carry_a = __shfl_sync(0xFFFFFFFFu, st, 31);
     }
+    if (ph && lane == 0) ph[5] = clock64();
     uint32_t carry_e = 320u, carry_nv = 0xFFFFu;
 #pragma unroll
     for (int k = 9; k >= 0; k--) {
@@ -310,6 +313,7 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
         carry_nv = __shfl_sync(0xFFFFFFFFu, v[k], 0);
         carry_e = __shfl_sync(0xFFFFFFFFu, en, 0);
     }
+    if (ph && lane == 0) ph[0] = clock64();
     // token decision per position
     uint32_t tsym[10], text[10];          // tsym 0xFF = no token here
 #pragma unroll
@@ -342,7 +346,9 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
         tsym[k] = sym; text[k] = ext;
     }
     __syncwarp();
+    if (ph && lane == 0) ph[1] = clock64();
     mf_build_code_warp<1>(H.clhist, 19, 7, H.cllens, H.clcodes, H.code, lane);
+    if (ph && lane == 0) ph[2] = clock64();
     // HCLEN
     const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     uint32_t ord = 0;
@@ -574,12 +580,9 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     MF_PHASE(9);
     uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
     if (warp == 0) {
-        uint32_t hb = mf_header_warp(S.ll_lens, S.d_lens, outw, S.whdr, lane);
+        uint32_t hb = mf_header_warp(S.ll_lens, S.d_lens, outw, S.whdr, lane, phase_clk ? &phase_clk[(size_t)c * 16 + 10] : nullptr);
         if (lane == 0) S.hdr_bits = hb;
     }
-    MF_PHASE(10);
-    MF_PHASE(11);
-    MF_PHASE(12);
     MF_PHASE(13);
     __syncthreads();
 

@@ -67,6 +67,7 @@ struct WaveCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_cmp = nullptr, ev_res = nullptr, ev_done = nullptr;
+    cudaEvent_t tl_start = nullptr, tl_in = nullptr, tl_res = nullptr, tl_done = nullptr;   // timeline (MFCAS_PHASE_TIMING)
     DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2;
     HostBuf h_desc, h_res;
     // bookkeeping of the submitted wave
@@ -136,6 +137,7 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
     CU(cudaEventCreateWithFlags(&W.ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_sha, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_cmp, cudaEventDisableTiming));
+    CU(cudaEventCreate(&W.tl_start)); CU(cudaEventCreate(&W.tl_in)); CU(cudaEventCreate(&W.tl_res)); CU(cudaEventCreate(&W.tl_done));
     CU(cudaEventCreateWithFlags(&W.ev_res, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
     return MFCAS_OK;
@@ -164,7 +166,7 @@ void device_teardown(DeviceState &D) {
         W.in_arena.release(); W.out_arena.release(); W.d_desc.release(); W.d_work.release(); W.slots.release();
         W.phase.release(); W.phase2.release(); W.h_desc.release(); W.h_res.release();
         for (auto &e : W.ev) if (e) cudaEventDestroy(e);
-        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_done}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_done, W.tl_start, W.tl_in, W.tl_res, W.tl_done}) if (e) cudaEventDestroy(e);
         if (W.stream) cudaStreamDestroy(W.stream);
         if (W.stream2) cudaStreamDestroy(W.stream2);
     }
@@ -342,13 +344,15 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
             CU(cudaMemcpy(h.data(), W.phase.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             // boundaries in program order: 0 start,1 loaded,2 crc,3 lz,8 litlen code,9 dist code,10 rle,11 zeroed,12 cl code,13 header,4,5,6,7
             static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
-            static const char *nm[13] = {"load", "crc", "lz77", "codes(warp0)", "codes_sync", "header", "-", "-", "-", "sync", "bitcount", "pack", "store"};
+            static const char *nm[13] = {"load", "crc", "lz77", "codes(warp0)", "codes_sync", "hdr_scan", "hdr_tokens", "hdr_clcode", "hdr_write", "sync", "bitcount", "pack", "store"};
             double acc[13] = {0};
             for (uint64_t c = 0; c < nc; c++)
                 for (int k = 0; k < 13; k++) acc[k] += (double)(h[c * 16 + seq[k + 1]] - h[c * 16 + seq[k]]);
             fprintf(stderr, "[mfcas phase] deflate, mean cycles per chunk over %llu chunks:", (unsigned long long)nc);
             for (int k = 0; k < 13; k++) fprintf(stderr, " %s=%.0f", nm[k], acc[k] / (double)nc);
-            fprintf(stderr, "\n");
+            double x0 = 0, x1 = 0, x2 = 0;
+            for (uint64_t c = 0; c < nc; c++) { x0 += (double)(h[c * 16 + 14] - h[c * 16 + 9]); x1 += (double)(h[c * 16 + 15] - h[c * 16 + 14]); x2 += (double)(h[c * 16 + 10] - h[c * 16 + 15]); }
+            fprintf(stderr, " | hdr_scan split: trim+fill=%.0f fwd=%.0f bwd=%.0f\n", x0 / (double)nc, x1 / (double)nc, x2 / (double)nc);
         }
     }
     return MFCAS_OK;
@@ -467,11 +471,14 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
         W.w_len[k] = io.src_len[i];
         up.add(io.src[i], (void *)W.w_src[k], io.src_len[i]);
     }
+    if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, W.stream));
     for (auto &it : up.items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, W.stream)); D.h2d += it.n; }
+    if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, W.stream));
     int rc;
     if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data());
     else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack);
     if (rc != MFCAS_OK) return rc;
+    if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));
     // Output copies are enqueued right behind the kernels, without a host round trip: the whole destination
     // slot (its capacity) is copied -- for packed output a few per cent more than the bytes produced, for decoded
     // output exactly the decoded size -- so that D2H of this wave overlaps H2D and kernels of the next ones.
@@ -481,6 +488,7 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
         for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, W.stream)); D.d2h += it.n; }
     }
     CU(cudaEventRecord(W.ev_done, W.stream));
+    if (phase_timing_on()) CU(cudaEventRecord(W.tl_done, W.stream));
     W.op = io.op; W.pos = pos; W.wn = wn; W.state = 1;
     return MFCAS_OK;
 }
@@ -544,6 +552,22 @@ int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
         int r2 = wave_drain(D, O, io);
         if (rc == MFCAS_OK) rc = r2;
     }
+    if (phase_timing_on() && w <= D.ring.size() && rc == MFCAS_OK) {
+        fprintf(stderr, "[mfcas timeline] %s, %zu waves (ms since first H2D): wave: h2d_start h2d_end | sha_start sha_end | enc_start enc_end | results | out_d2h_end\n",
+                io.op == Op::Unpack ? "unpack" : "pack", w);
+        cudaEvent_t t0 = D.ring[0].tl_start;
+        for (size_t k = 0; k < w; k++) {
+            WaveCtx &O = D.ring[k];
+            float a = 0, b = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, e = 0, f = 0;
+            cudaEventElapsedTime(&a, t0, O.tl_start); cudaEventElapsedTime(&b, t0, O.tl_in);
+            if (io.op != Op::Unpack) { cudaEventElapsedTime(&c0, t0, O.ev[0]); cudaEventElapsedTime(&c1, t0, O.ev[1]); }
+            if (io.op == Op::Pack) { cudaEventElapsedTime(&d0, t0, O.ev[2]); cudaEventElapsedTime(&d1, t0, O.ev[4]); }
+            if (io.op == Op::Unpack) { cudaEventElapsedTime(&d0, t0, O.ev[5]); cudaEventElapsedTime(&d1, t0, O.ev[7]); }
+            cudaEventElapsedTime(&e, t0, O.tl_res); cudaEventElapsedTime(&f, t0, O.tl_done);
+            fprintf(stderr, "  %2zu: %6.1f %6.1f | %6.1f %6.1f | %6.1f %6.1f | %6.1f | %6.1f\n", k, a, b, c0, c1, d0, d1, e, f);
+        }
+        (void)cudaGetLastError();
+    }
     return rc;
 }
 
@@ -589,6 +613,9 @@ int mfcas_device_count(void) {
 }
 
 mfcas_ctx *mfcas_create(const int *devices, int ndev, uint64_t wave_bytes, uint32_t flags) {
+    // Every in-flight wave has its own streams; with the default of 8 hardware work queues they alias and
+    // serialise (wave k+4's H2D waits for wave k's SHA-1).  Effective only if set before the CUDA context exists.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int avail = mfcas_device_count();
     if (avail <= 0) return nullptr;
     if (ndev <= 0) ndev = avail;
