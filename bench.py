@@ -6,7 +6,8 @@ N(0,1) numpy array (pickle protocol 4 -> 16,777,379-byte blob).  One STEP = one 
 `--blobs-per-step` such blobs per GPU going through the whole hot path:
     save: SHA-1 key + DEFLATE + CRC-32 -> RFC 1952 file      (mfcas_pack_*)
     load: INFLATE + CRC-32/ISIZE verification -> blob bytes  (mfcas_unpack_*)
-With the defaults (512 blobs/step, 8 steps) the job is exactly the 4096 blobs.  Round-robin sharding:
+With the defaults (1024 blobs/step, 4 steps) the job is exactly the 4096 blobs (SHA-1 is one serial chain
+per blob, so the wave is made as wide as HBM allows: 1024 concurrent chains).  Round-robin sharding:
 blob i of the global batch belongs to rank i mod N (weak scaling: per-GPU wave size is fixed).
 
   value : round-trip GB/s with inputs/outputs resident in HBM (mfcas_pack_device / _unpack_device),
@@ -368,10 +369,10 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blobs-per-step", type=int, default=512)
+    ap.add_argument("--blobs-per-step", type=int, default=1024)
     ap.add_argument("--wave-mib", type=int, default=2048, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -174,13 +174,32 @@ void device_teardown(DeviceState &D) {
     if (D.compute) { cudaStreamSynchronize(D.compute); cudaStreamDestroy(D.compute); D.compute = nullptr; }
 }
 
+// Copies a set of (host ptr, device ptr, len) with runs of contiguous pairs merged into one memcpy.
+struct CopyPlan {
+    struct Item { char *h; char *d; size_t n; };
+    std::vector<Item> items;
+    void add(const void *h, void *d, size_t n) {
+        if (!n) return;
+        char *hc = (char *)h, *dc = (char *)d;
+        if (!items.empty()) {
+            Item &l = items.back();
+            ptrdiff_t gh = hc - l.h, gd = dc - l.d;
+            // same displacement on both sides and the gap after the previous item is small: extend
+            if (gh == gd && gh >= (ptrdiff_t)l.n && gh - (ptrdiff_t)l.n <= 4096) { l.n = (size_t)gh + n; return; }
+        }
+        items.push_back({hc, dc, n});
+    }
+};
+
 static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMING") != nullptr; return on; }
 
 // ------------------------------------------------------------------ pack: enqueue (async) / collect
 // Inputs and outputs are DEVICE pointers.  Everything is enqueued on W's streams, including the copy of the
 // small result block (dst_len, status, digests) to pinned host memory; W.ev_res fires when that is there.
+// `upload` (host-pointer API): the wave's input copies; they are enqueued AFTER the small descriptor copy so
+// that nothing small ever queues behind other waves' gigabyte copies on the copy engine.
 int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                void *const *d_dst, const uint64_t *dst_cap, bool want_pack) {
+                void *const *d_dst, const uint64_t *dst_cap, bool want_pack, const CopyPlan *upload) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
@@ -260,6 +279,11 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(dres + W.r_st, 0, sizeof(int32_t) * n, s));
+    if (upload) {
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
+        for (auto &it : upload->items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, s)); D.h2d += it.n; }
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
+    }
     CU(cudaEventRecord(W.ev_in, s));
     // ---- SHA-1 on the high-priority second stream (serial per blob: it overlaps the chunk-parallel encoder)
     CU(cudaStreamWaitEvent(s2, W.ev_in, 0));
@@ -360,7 +384,7 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
 
 // ------------------------------------------------------------------ unpack: enqueue (async) / collect
 int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                  void *const *d_dst, const uint64_t *dst_cap) {
+                  void *const *d_dst, const uint64_t *dst_cap, const CopyPlan *upload) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t max_chunks = 0, max_members = 0;
     for (uint64_t i = 0; i < n; i++) { max_chunks += dst_cap[i] / MF_CHUNK + 1; max_members += dst_cap[i] / MF_MEMBER_RAW + 2; }
@@ -391,6 +415,11 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     cudaStream_t s = W.stream;
     CU(cudaMemcpyAsync(W.d_desc.p, hb, sizeof(MfDecBlob) * n, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + W.res_bytes) - o_kind, s));     // kind, counters, dst_len, status
+    if (upload) {
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
+        for (auto &it : upload->items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, s)); D.h2d += it.n; }
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
+    }
     const MfDecBlob *db = W.d_desc.as<MfDecBlob>();
     MfDecCounters *cnt = reinterpret_cast<MfDecCounters *>(dw + o_cnt);
     CU(cudaEventRecord(W.ev[5], s));
@@ -431,23 +460,6 @@ struct Shard {
     std::vector<uint64_t> idx;     // blob indices of this device, in order
 };
 
-// Copies a set of (host ptr, device ptr, len) with runs of contiguous pairs merged into one memcpy.
-struct CopyPlan {
-    struct Item { char *h; char *d; size_t n; };
-    std::vector<Item> items;
-    void add(const void *h, void *d, size_t n) {
-        if (!n) return;
-        char *hc = (char *)h, *dc = (char *)d;
-        if (!items.empty()) {
-            Item &l = items.back();
-            ptrdiff_t gh = hc - l.h, gd = dc - l.d;
-            // same displacement on both sides and the gap after the previous item is small: extend
-            if (gh == gd && gh >= (ptrdiff_t)l.n && gh - (ptrdiff_t)l.n <= 4096) { l.n = (size_t)gh + n; return; }
-        }
-        items.push_back({hc, dc, n});
-    }
-};
-
 struct ShardIO {
     Op op; const Shard *sh;
     const void *const *src; const uint64_t *src_len; void *const *dst; const uint64_t *dst_cap;
@@ -471,12 +483,9 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
         W.w_len[k] = io.src_len[i];
         up.add(io.src[i], (void *)W.w_src[k], io.src_len[i]);
     }
-    if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, W.stream));
-    for (auto &it : up.items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, W.stream)); D.h2d += it.n; }
-    if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, W.stream));
     int rc;
-    if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data());
-    else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack);
+    if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), &up);
+    else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack, &up);
     if (rc != MFCAS_OK) return rc;
     if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));
     // Output copies are enqueued right behind the kernels, without a host round trip: the whole destination
@@ -705,7 +714,7 @@ int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *cons
     if (n == 0) return MFCAS_OK;
     cudaSetDevice(D.dev);
     WaveCtx &W = D.ring[0];
-    int rc = pack_submit(D, W, ctx->flags, n, d_src, src_len, d_dst, dst_cap, true);
+    int rc = pack_submit(D, W, ctx->flags, n, d_src, src_len, d_dst, dst_cap, true, nullptr);
     if (rc == MFCAS_OK) rc = pack_collect(D, W, dst_len, sha1, status);
     if (rc != MFCAS_OK) ctx->err = D.err;
     return rc;
@@ -720,7 +729,7 @@ int mfcas_unpack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *co
     if (n == 0) return MFCAS_OK;
     cudaSetDevice(D.dev);
     WaveCtx &W = D.ring[0];
-    int rc = unpack_submit(D, W, n, d_src, src_len, d_dst, dst_cap);
+    int rc = unpack_submit(D, W, n, d_src, src_len, d_dst, dst_cap, nullptr);
     if (rc == MFCAS_OK) rc = unpack_collect(D, W, dst_len, status);
     if (rc != MFCAS_OK) ctx->err = D.err;
     return rc;

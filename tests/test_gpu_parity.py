@@ -220,6 +220,22 @@ def test_baseline_size_properties(gpu_codec):
     assert ratio < 0.935
 
 
+def test_many_small_blobs_dense_sha_mode(gpu_codec):
+    """More than 296 SHA-1 CTAs (> 9472 blobs) switches the hash kernel to its densely packed mode;
+    BASELINE config C3 shape (many small, hash-bound blobs) at reduced count."""
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal(2048 * 3, dtype=np.float32).tobytes()
+    blobs = [base[(i % 97):(i % 97) + 4096 + (i % 13)] + i.to_bytes(4, "little") for i in range(12000)]
+    keys, packed = gpu_codec.pack_batch(blobs)
+    packed = [bytes(p) for p in packed]
+    assert keys == [hashlib.sha1(b).hexdigest() for b in blobs]
+    for i in (0, 1, 5999, 11999):
+        assert gzip.decompress(packed[i]) == blobs[i]
+    back = gpu_codec.unpack_batch(packed)
+    assert all(o == b for o, b in zip(back, blobs))
+    assert gpu_codec.hash_batch(blobs[:5000]) == keys[:5000]
+
+
 def test_device_resident_api(gpu_codec):
     import torch
     from metaflow_b200 import capi
