@@ -8,8 +8,9 @@
 //   mf_inflate_chunk_kernel  one warp per 32 KiB chunk, one LANE per 1 KiB segment: lane 0 parses the
 //                            block header, the warp builds lookup tables with match.any ranks, then
 //                            32 lanes Huffman-decode 32 segments concurrently (the index gives every
-//                            segment's bit offset; LZ77 matches never leave a segment), output staged
-//                            in padded shared-memory rows, CRC-32 per lane, coalesced stores to HBM
+//                            segment's bit offset; LZ77 matches never leave a segment); each lane writes
+//                            its segment to HBM 16 bytes at a time from registers and folds the CRC-32
+//                            in on the way (no shared-memory staging: registers bound the occupancy)
 //   mf_verify_kernel         one warp per member: GF(2)-combine the chunk CRCs, compare with trailer
 //   mf_gunzip_lane_kernel    foreign streams (stock Metaflow / zlib level 3 writers): a DEFLATE stream
 //                            without an index is bit-serial, so one lane decodes one whole blob
@@ -125,15 +126,13 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
 }
 
 // ------------------------------------------------------------------ chunk decoder
-#define MF_DEC_WARPS 2
-#define MF_ROW (MF_SEG + 4u)          // padded row: lanes writing the same column hit distinct banks
+#define MF_DEC_WARPS 8
 #define MF_LL_LUT_BITS 10
 #define MF_D_LUT_BITS 8
 
 struct MfCanonSmall { uint16_t count[16]; uint16_t symbol[32]; };
 
 struct __align__(16) MfDecWarpSmem {
-    uint8_t out[MF_SEGS_PER_CHUNK * MF_ROW];
     uint16_t lut_ll[1u << MF_LL_LUT_BITS];   // sym | len << 9 ; 0 = code longer than the LUT
     uint16_t lut_d[1u << MF_D_LUT_BITS];     // sym | len << 5
     uint8_t lens[320];
@@ -146,8 +145,65 @@ struct __align__(16) MfDecWarpSmem {
     uint32_t hlit, hdist, hdr_end;
 };
 struct __align__(16) MfDecSmem {
-    uint32_t crc_tab[256];
+    uint32_t crc_tab[4][256];         // slice-by-4
     MfDecWarpSmem w[MF_DEC_WARPS];
+};
+
+// Per-lane output writer: decoded bytes go straight to the lane's 1 KiB segment in HBM, 16 bytes at a
+// time from registers; the raw CRC-32 (slice-by-4) is folded in as every 4-byte word completes.  No
+// shared-memory staging of the output: what limits resident decoder lanes is registers, not smem.
+struct MfLaneWriter {
+    uint8_t *dst;        // segment base in global memory
+    uint32_t op;         // bytes produced
+    uint32_t w[4];       // the current 16-byte window (valid while `vec`)
+    uint32_t cw, cn;     // CRC: pending word and number of bytes in it
+    uint32_t crc;
+    bool vec;            // window mode possible (dst 16-byte aligned and op at a 16-byte boundary when it started)
+    __device__ __forceinline__ void init(uint8_t *d) { dst = d; op = 0; w[0] = w[1] = w[2] = w[3] = 0; cw = 0; cn = 0; crc = 0; vec = (((uintptr_t)d & 15u) == 0); }
+    __device__ __forceinline__ void crc_byte(uint32_t b, const uint32_t (*T)[256]) {
+        cw |= b << (8u * cn);
+        if (++cn == 4) {
+            uint32_t x = crc ^ cw;
+            crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24];
+            cw = 0; cn = 0;
+        }
+    }
+    __device__ __forceinline__ void put(uint32_t b, const uint32_t (*T)[256]) {
+        crc_byte(b, T);
+        if (vec) {
+            const uint32_t k = op & 15u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) if ((int)(k >> 2) == j) w[j] |= b << (8u * (k & 3u));
+            op++;
+            if ((op & 15u) == 0) {
+                *reinterpret_cast<uint4 *>(dst + op - 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                w[0] = w[1] = w[2] = w[3] = 0;
+            }
+        } else {
+            dst[op++] = (uint8_t)b;
+            if ((op & 15u) == 0 && (((uintptr_t)dst & 15u) == 0)) vec = true;      // realigned: back to window mode
+        }
+    }
+    // bytes of the open window reach memory (needed before a match reads them back, and at the end)
+    __device__ __forceinline__ void spill_window() {
+        if (vec) {
+            const uint32_t k = op & 15u, base = op - k;
+            for (uint32_t j = 0; j < k; j++) dst[base + j] = (uint8_t)(w[j >> 2] >> (8u * (j & 3u)));
+            w[0] = w[1] = w[2] = w[3] = 0;
+            if (k) vec = false;           // continue with byte stores until the next 16-byte boundary
+        }
+    }
+    __device__ __forceinline__ void copy_match(uint32_t len, uint32_t dist, const uint32_t (*T)[256]) {
+        spill_window();
+        for (uint32_t k = 0; k < len; k++) { uint32_t b = dst[op - dist]; put(b, T); }
+    }
+    __device__ __forceinline__ uint32_t finish(const uint32_t (*T)[256]) {
+        spill_window();
+        // CRC tail: fewer than 4 pending bytes
+        for (uint32_t j = 0; j < cn; j++) crc = T[0][(crc ^ (cw >> (8u * j))) & 0xFFu] ^ (crc >> 8);
+        cn = 0;
+        return crc;
+    }
 };
 
 struct MfFastReader {
@@ -191,14 +247,17 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfDecSmem &S = *reinterpret_cast<MfDecSmem *>(mf_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) S.crc_tab[i] = g_mf_crc_tab[0][i];
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
     __syncthreads();
     const uint32_t c = blockIdx.x * MF_DEC_WARPS + warp;
     if (c >= counters->n_chunks) return;
     MfDecWarpSmem &W = S.w[warp];
     const MfDecChunk ch = chunks[c];
     const uint32_t raw_len = ch.raw_len;
+    const uint32_t seg_base = lane * MF_SEG;
+    const uint32_t seglen = seg_base < raw_len ? min((uint32_t)MF_SEG, raw_len - seg_base) : 0u;
     int err = 0;
+    uint32_t crc = 0;
 
     if (ch.hdr_bits == MF_STORED_MARK) {
         // 00 | LEN | NLEN | raw bytes
@@ -210,13 +269,12 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
         }
         __syncwarp();
         err = W.err;
-        if (!err) {
-            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
-                uint32_t base = r * MF_SEG;
-                for (uint32_t k = lane; k < MF_SEG && base + k < raw_len; k += 32) W.out[r * MF_ROW + k] = ch.src[5u + base + k];
-            }
+        if (!err && seglen) {
+            MfLaneWriter wr; wr.init(ch.dst + seg_base);
+            const uint8_t *sp = ch.src + 5u + seg_base;
+            for (uint32_t k = 0; k < seglen; k++) wr.put(sp[k], S.crc_tab);
+            crc = wr.finish(S.crc_tab);
         }
-        __syncwarp();
     } else {
         // ---- block header (lane 0), lengths into smem
         if (lane == 0) {
@@ -300,23 +358,20 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
             // ---- 32 lanes decode 32 segments
             const uint32_t mybits = mf_le16(ch.segidx + 2u * lane);
             const uint32_t incl = mf_warp_incl_scan(mybits, lane);
-            const uint32_t seg_base = lane * MF_SEG;
             int lerr = 0;
             const uint32_t allbits = __shfl_sync(0xFFFFFFFFu, incl, 31);
             if ((uint64_t)ch.hdr_bits + allbits > (uint64_t)ch.comp_bytes * 8ull) lerr = MF_DEC_E_STREAM;   // index points past the chunk
-            else if (seg_base < raw_len) {
-                const uint32_t seglen = min((uint32_t)MF_SEG, raw_len - seg_base);
-                uint8_t *row = W.out + lane * MF_ROW;
+            else if (seglen) {
+                MfLaneWriter wr; wr.init(ch.dst + seg_base);
                 MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits);
-                uint32_t op = 0;
-                while (op < seglen) {
+                while (wr.op < seglen) {
                     if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
                     br.fill();
                     uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
                     int sym;
                     if (e) { sym = (int)(e & 511u); br.drop(e >> 9); }
                     else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
-                    if (sym < 256) { row[op++] = (uint8_t)sym; continue; }
+                    if (sym < 256) { wr.put((uint32_t)sym, S.crc_tab); continue; }
                     if (sym == 256 || sym > 285) { lerr = MF_DEC_E_STREAM; break; }
                     br.fill();
                     sym -= 257;
@@ -329,10 +384,11 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                     if (ds >= 30) { lerr = MF_DEC_E_STREAM; break; }
                     br.fill();
                     uint32_t dist = mf_dbase(ds) + br.get(mf_dext(ds));
-                    if (dist > op || op + len > seglen) { lerr = MF_DEC_E_STREAM; break; }
-                    for (uint32_t k = 0; k < len; k++) { row[op] = row[op - dist]; op++; }
+                    if (dist > wr.op || wr.op + len > seglen) { lerr = MF_DEC_E_STREAM; break; }
+                    wr.copy_match(len, dist, S.crc_tab);
                 }
                 if (!lerr && br.used != mybits) lerr = MF_DEC_E_STREAM;
+                crc = wr.finish(S.crc_tab);
             } else if (mybits != 0) lerr = MF_DEC_E_STREAM;
             if (__any_sync(0xFFFFFFFFu, lerr != 0)) err = MF_DEC_E_STREAM;
         }
@@ -340,52 +396,14 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     }
     if (err) { if (lane == 0) { mf_set_status(status, ch.blob, err); chunk_crc[c] = 0; } return; }
 
-    // ---- CRC-32 of the chunk: one 1 KiB row per lane, then GF(2) shift + xor-reduce
-    {
-        const uint32_t seg_base = lane * MF_SEG;
-        uint32_t crc = 0;
-        if (seg_base < raw_len) {
-            const uint32_t seglen = min((uint32_t)MF_SEG, raw_len - seg_base);
-            const uint8_t *row = W.out + lane * MF_ROW;
-            const uint32_t *rw = reinterpret_cast<const uint32_t *>(row);
-            uint32_t nw = seglen >> 2;
-            for (uint32_t i = 0; i < nw; i++) {
-                uint32_t x = rw[i];
-                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
-                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
-                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8); x >>= 8;
-                crc = S.crc_tab[(crc ^ x) & 0xFFu] ^ (crc >> 8);
-            }
-            for (uint32_t p = nw << 2; p < seglen; p++) crc = S.crc_tab[(crc ^ row[p]) & 0xFFu] ^ (crc >> 8);
-            uint32_t after = raw_len - (seg_base + seglen);
-            uint32_t mul = ((after & 63u) == 0) ? g_mf_piece_mul[after >> 6] : mf_xpow8(after);
-            crc = mf_gf2_mul(crc, mul);
-        }
-        crc = mf_warp_xor(crc);
-        if (lane == 0) chunk_crc[c] = crc;
+    // ---- chunk CRC: every lane's segment CRC shifted by the bytes that follow it, xor-reduced
+    if (seglen) {
+        uint32_t after = raw_len - (seg_base + seglen);
+        uint32_t mul = ((after & 63u) == 0) ? g_mf_piece_mul[after >> 6] : mf_xpow8(after);
+        crc = mf_gf2_mul(crc, mul);
     }
-    // ---- rows -> HBM
-    {
-        uint8_t *dst = ch.dst;
-        if (((uintptr_t)dst & 3u) == 0) {
-            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
-                uint32_t base = r * MF_SEG;
-                if (base >= raw_len) break;
-                uint32_t seglen = min((uint32_t)MF_SEG, raw_len - base);
-                const uint32_t *rw = reinterpret_cast<const uint32_t *>(W.out + r * MF_ROW);
-                uint32_t *dw = reinterpret_cast<uint32_t *>(dst + base);
-                uint32_t nw = seglen >> 2;
-                for (uint32_t i = lane; i < nw; i += 32) dw[i] = rw[i];
-                uint32_t tail = seglen & 3u;
-                if (lane < tail) dst[base + (nw << 2) + lane] = W.out[r * MF_ROW + (nw << 2) + lane];
-            }
-        } else {
-            for (uint32_t r = 0; r < MF_SEGS_PER_CHUNK; r++) {
-                uint32_t base = r * MF_SEG;
-                for (uint32_t k = lane; k < MF_SEG && base + k < raw_len; k += 32) dst[base + k] = W.out[r * MF_ROW + k];
-            }
-        }
-    }
+    crc = mf_warp_xor(crc);
+    if (lane == 0) chunk_crc[c] = crc;
 }
 
 __global__ void __launch_bounds__(128)
