@@ -195,7 +195,9 @@ struct MfLaneWriter {
     }
     __device__ __forceinline__ void copy_match(uint32_t len, uint32_t dist, const uint32_t (*T)[256]) {
         spill_window();
-        for (uint32_t k = 0; k < len; k++) { uint32_t b = dst[op - dist]; put(b, T); }
+        vec = false;                      // the source may be the bytes just written: everything goes through memory
+        for (uint32_t k = 0; k < len; k++) { uint32_t b = dst[op - dist]; crc_byte(b, T); dst[op++] = (uint8_t)b; }
+        if ((op & 15u) == 0 && (((uintptr_t)dst & 15u) == 0)) vec = true;
     }
     __device__ __forceinline__ uint32_t finish(const uint32_t (*T)[256]) {
         spill_window();

@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30
+echo "=== bench (default 1024 x 2 steps)"; timeout 1500 python bench.py --steps 2 --warmup 1 --no-cpu-baseline
+} > gpurun_out/run8.log 2>&1
+tail -c 5000 gpurun_out/run8.log
