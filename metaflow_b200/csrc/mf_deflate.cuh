@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t mf_crc_words(const uint8_t *s, uint32_t off,
 // greedy order replaced by 256 benefit/cost buckets (one scan per round instead of a sort) and an exact
 // completion step, so no loop is longer than K and nothing waits on a CTA barrier.
 struct MfWarpCodeScratch {
-    uint32_t bcost[256];     // code space wanted per benefit/cost bucket
+    uint32_t bcost[32];      // code space wanted per benefit/cost bucket
     uint32_t lcnt[16];       // codes per length
     uint32_t nxt[16];        // next canonical code per length
 };
@@ -155,9 +155,9 @@ __device__ __forceinline__ void mf_build_code_warp(const uint32_t *hist, int n, 
         mass -= full >> newl;
     }
     uint32_t slack = full - mass;
-    const float inv_t = 256.0f / (float)T;
+    const float inv_t = 32.0f / (float)T;
     for (int round = 0; round < 3 && slack; round++) {
-        for (uint32_t i = lane; i < 256; i += 32) W.bcost[i] = 0;
+        W.bcost[lane] = 0;
         __syncwarp();
         uint32_t bk[K];
 #pragma unroll
@@ -165,34 +165,22 @@ __device__ __forceinline__ void mf_build_code_warp(const uint32_t *hist, int n, 
             bk[k] = 0xFFFFFFFFu;
             if (l[k] > 1) {
                 uint32_t key = f[k] << l[k];                     // in [T, 2T) unless the length was clamped
-                uint32_t b = key > T ? min(255u, (uint32_t)((float)(key - T) * inv_t)) : 0u;
+                uint32_t b = key > T ? min(31u, (uint32_t)((float)(key - T) * inv_t)) : 0u;
                 bk[k] = b;
                 atomicAdd(&W.bcost[b], full >> l[k]);
             }
         }
         __syncwarp();
-        // lane j owns buckets 255-8j .. 248-8j (descending benefit); accept the longest prefix that fits
-        uint32_t c[8], lsum = 0;
+        // lane j owns bucket 31-j (descending benefit/cost); accept the longest prefix of buckets that fits
+        uint32_t cum = W.bcost[31 - lane];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { c[j] = W.bcost[255 - 8 * (int)lane - j]; lsum += c[j]; }
-        uint32_t incl = lsum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d); if ((int)lane >= d) incl += u; }
-        uint32_t cum = incl - lsum, thr_local = 0;
-        bool rejected = false;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (!rejected) {
-                if (cum + c[j] <= slack) cum += c[j];
-                else { rejected = true; thr_local = 256u - 8u * lane - (uint32_t)j; }   // first rejected bucket + 1
-            }
-        }
-        const uint32_t rej = __ballot_sync(0xFFFFFFFFu, rejected);
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, cum, d); if ((int)lane >= d) cum += u; }
+        const uint32_t rej = __ballot_sync(0xFFFFFFFFu, cum > slack);
         uint32_t thr = 0, consumed;
         if (rej) {
-            const int L = __ffs(rej) - 1;
-            thr = __shfl_sync(0xFFFFFFFFu, thr_local, L);
-            consumed = __shfl_sync(0xFFFFFFFFu, cum, L);
+            const int L = __ffs(rej) - 1;                         // first bucket (in descending order) that does not fit
+            thr = 32u - (uint32_t)L;
+            consumed = L ? __shfl_sync(0xFFFFFFFFu, cum, L - 1) : 0u;
         } else {
             consumed = __shfl_sync(0xFFFFFFFFu, cum, 31);
         }
@@ -231,10 +219,10 @@ __device__ __forceinline__ void mf_build_code_warp(const uint32_t *hist, int n, 
         __syncwarp();
     }
     // canonical codes (RFC 1951 3.2.2): first code per length, then rank among equal lengths in symbol order
-    if (lane == 0) {
+    if (lane < 16) {                      // first code of length `lane`: sum_{j<lane} cnt[j] << (lane - j)
         uint32_t code = 0;
-        W.nxt[0] = 0;
-        for (int b = 1; b <= 15; b++) { code = (code + (b - 1 >= 1 ? W.lcnt[b - 1] : 0u)) << 1; W.nxt[b] = code; }
+        for (uint32_t j = 1; j < lane; j++) code += W.lcnt[j] << (lane - j);
+        W.nxt[lane] = code;
     }
     __syncwarp();
 #pragma unroll
@@ -281,37 +269,34 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
     if (lane < 32) H.clhist[lane] = 0;
     __syncwarp();
     if (ph && lane == 0) ph[4] = clock64();
-    // run start a(p) (forward max-scan of start positions) and run end e(p) (backward min-scan), rows k = p / 32
-    uint32_t v[10], a[10], e[10];
-    uint32_t carry_v = 0xFFFFu, carry_a = 0;
+    // run start a(p) and run end e(p) from ballots of "a run starts here" flags (rows k = p / 32): no scan,
+    // no carried dependency between rows except two uniform register chains
+    uint32_t v[10], m[10];
 #pragma unroll
     for (int k = 0; k < 10; k++) {
         const int p = k * 32 + (int)lane;
-        v[k] = p < n ? H.seq[p] : (0x100u + (uint32_t)(p & 1));          // sentinels never form runs with data
-        uint32_t prev = __shfl_up_sync(0xFFFFFFFFu, v[k], 1);
-        if (lane == 0) prev = carry_v;
-        uint32_t st = (v[k] != prev) ? (uint32_t)p : 0u;
-        if (lane == 0 && st == 0) st = carry_a;                           // run continues from the previous row
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xFFFFFFFFu, st, d); if ((int)lane >= d) st = max(st, u); }
-        a[k] = st;
-        carry_v = __shfl_sync(0xFFFFFFFFu, v[k], 31);
-        carry_a = __shfl_sync(0xFFFFFFFFu, st, 31);
+        const uint32_t cur = p < n ? H.seq[p] : 0x100u;
+        const uint32_t prev = (p > 0 && p <= n) ? H.seq[p - 1] : 0x200u;
+        v[k] = cur;
+        m[k] = __ballot_sync(0xFFFFFFFFu, p >= n || p == 0 || cur != prev);
     }
     if (ph && lane == 0) ph[5] = clock64();
-    uint32_t carry_e = 320u, carry_nv = 0xFFFFu;
+    uint32_t a[10], e[10];
+    {
+        uint32_t last = 0;                                    // last start before row k
 #pragma unroll
-    for (int k = 9; k >= 0; k--) {
-        const int p = k * 32 + (int)lane;
-        uint32_t nxtv = __shfl_down_sync(0xFFFFFFFFu, v[k], 1);
-        if (lane == 31) nxtv = carry_nv;
-        uint32_t en = (v[k] != nxtv) ? (uint32_t)(p + 1) : 0xFFFFu;       // run ends right after p
-        if (lane == 31 && en == 0xFFFFu) en = carry_e;
+        for (int k = 0; k < 10; k++) {
+            const uint32_t below = m[k] & (0xFFFFFFFFu >> (31u - lane));          // starts at lanes <= mine
+            a[k] = below ? (uint32_t)(k * 32 + 31 - __clz((int)below)) : last;
+            if (m[k]) last = (uint32_t)(k * 32 + 31 - __clz((int)m[k]));
+        }
+        uint32_t nxt = 320u;                                  // first start after row k
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_down_sync(0xFFFFFFFFu, en, d); if ((int)lane + d < 32) en = min(en, u); }
-        e[k] = en;
-        carry_nv = __shfl_sync(0xFFFFFFFFu, v[k], 0);
-        carry_e = __shfl_sync(0xFFFFFFFFu, en, 0);
+        for (int k = 9; k >= 0; k--) {
+            const uint32_t above = lane == 31 ? 0u : (m[k] & (0xFFFFFFFFu << (lane + 1u)));   // starts at lanes > mine
+            e[k] = above ? (uint32_t)(k * 32 + __ffs((int)above) - 1) : nxt;
+            if (m[k]) nxt = (uint32_t)(k * 32 + __ffs((int)m[k]) - 1);
+        }
     }
     if (ph && lane == 0) ph[0] = clock64();
     // token decision per position
