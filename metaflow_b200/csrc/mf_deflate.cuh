@@ -394,6 +394,7 @@ struct __align__(16) MfEncSmem {
     MfWarpHdrScratch whdr;           // warp 0: litlen code, then the block header
     MfWarpCodeScratch wdist;         // warp 1: distance code
     uint32_t hdr_bits;
+    uint32_t ticket;
     uint32_t nmatch[MF_SEGS_PER_CHUNK];
     uint32_t seg_bits[MF_SEGS_PER_CHUNK];
     uint32_t seg_off[MF_SEGS_PER_CHUNK];
@@ -409,13 +410,19 @@ __global__ void __launch_bounds__(MF_ENC_THREADS, 2)
 mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__restrict__ chunk_member, uint32_t n_chunks_total,
                   uint8_t *__restrict__ slots, uint32_t *__restrict__ comp_bytes_out, uint16_t *__restrict__ hdr_bits_out,
                   uint16_t *__restrict__ seg_bits_out, uint32_t *__restrict__ chunk_crc_out, uint32_t flags,
-                  unsigned long long *__restrict__ phase_clk) {
+                  unsigned long long *__restrict__ phase_clk, uint32_t *__restrict__ ticket) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfEncSmem &S = *reinterpret_cast<MfEncSmem *>(mf_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     // persistent CTAs: the grid is capped below 2 CTAs x 148 SMs (host side) so that some SMs always keep
     // a free slot for the latency-critical SHA-1 CTAs of this and the following waves
-    for (uint32_t c = blockIdx.x; c < n_chunks_total; c += gridDim.x) {
+    // Chunks are handed out by an atomic ticket, not by a static stride: CTAs that share their SM with SHA-1
+    // CTAs run slower, and a static partition would make everyone wait for them.
+    for (;;) {
+        if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t c = S.ticket;
+        if (c >= n_chunks_total) break;
     // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
 #define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 16 + (k)] = clock64(); } while (0)
     MF_PHASE(0);

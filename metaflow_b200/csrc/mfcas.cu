@@ -258,6 +258,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     const size_t o_seg = wc.take(sizeof(uint16_t) * n_chunks * MF_SEGS_PER_CHUNK);
     const size_t o_crc = wc.take(sizeof(uint32_t) * n_chunks);
     const size_t o_cdst = wc.take(sizeof(uint64_t) * n_chunks);
+    const size_t o_ticket = wc.take(sizeof(uint32_t));
     const size_t o_res = wc.take(0);
     Carver rc;
     W.r_len = rc.take(sizeof(uint64_t) * n, 16);
@@ -279,6 +280,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(dres + W.r_st, 0, sizeof(int32_t) * n, s));
+    CU(cudaMemsetAsync(dw + o_ticket, 0, sizeof(uint32_t), s));
     if (upload) {
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
         for (auto &it : upload->items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, s)); D.h2d += it.n; }
@@ -308,7 +310,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, MF_ENC_GRID_CAP), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
-                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase);
+                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket));
             CU(cudaGetLastError());
             D.launches++;
         }
