@@ -449,24 +449,6 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     __syncthreads();
 
     MF_PHASE(1);
-    // ---- pass 1: CRC-32 (raw, zero init) of the chunk; piece g = 64 bytes [64g, 64g+64)
-    {
-        uint32_t g = tid;                       // 512 pieces
-        uint32_t start = g * 64u;
-        uint32_t crc = 0;
-        if (start < len) {
-            uint32_t end = min(start + 64u, len);
-            uint32_t nw = (end - start) & ~3u;
-            crc = mf_crc_words(S.data, start, nw, S.crc_tab);
-            for (uint32_t p = start + nw; p < end; p++) crc = S.crc_tab[0][(crc ^ S.data[p]) & 0xFFu] ^ (crc >> 8);
-            uint32_t after = len - end;          // bytes of the chunk after this piece
-            uint32_t mul = (len == MF_CHUNK) ? g_mf_piece_mul[511u - g] : mf_xpow8(after);
-            crc = mf_gf2_mul(crc, mul);
-        }
-        crc = mf_warp_xor(crc);
-        if (lane == 0) S.crc_part[warp] = crc;
-    }
-
     MF_PHASE(2);
     // ---- pass 2: LZ77 over this warp's two segments
     {
@@ -559,40 +541,54 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
 
     MF_PHASE(3);
     // ---- pass 3: Huffman codes, block header
-    // warp 0: literal/length code; warp 1: distance code; everyone else zeroes region B (dead as hash tables
-    // now) for the bit writers.  No CTA barrier inside, and no loop longer than 10 iterations.
-    if (warp == 0) mf_build_code_warp<9>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.whdr.code, lane);
-    else if (warp == 1) mf_build_code_warp<1>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.wdist, lane);
+    // warp 0: literal/length code; warp 1: distance code (warp-synchronous, in registers); warps 2..15 meanwhile
+    // zero region B (dead as hash tables now) for the bit writers and compute the chunk's CRC-32
+    // (64-byte piece per lane, slice-by-4 tables in smem, GF(2) shift to the piece's position, xor-reduce).
+    if (warp == 0) { mf_build_code_warp<9>(S.ll_hist, 286, 15, S.ll_lens, S.ll_codes, S.whdr.code, lane); if (lane == 0) S.crc_part[0] = 0; }
+    else if (warp == 1) { mf_build_code_warp<1>(S.d_hist, 30, 15, S.d_lens, S.d_codes, S.wdist, lane); if (lane == 0) S.crc_part[1] = 0; }
     else {
         uint4 *z = reinterpret_cast<uint4 *>(S.regionB);
         for (uint32_t i = tid - 64; i < MF_REGION_B / 16; i += MF_ENC_THREADS - 64) z[i] = make_uint4(0, 0, 0, 0);
+        uint32_t acc = 0;
+        for (uint32_t g = tid - 64; g < 512u; g += MF_ENC_THREADS - 64) {
+            const uint32_t start = g * 64u;
+            if (start < len) {
+                const uint32_t end = min(start + 64u, len);
+                const uint32_t nw = (end - start) & ~3u;
+                uint32_t crc = mf_crc_words(S.data, start, nw, S.crc_tab);
+                for (uint32_t p = start + nw; p < end; p++) crc = S.crc_tab[0][(crc ^ S.data[p]) & 0xFFu] ^ (crc >> 8);
+                const uint32_t mul = (len == MF_CHUNK) ? g_mf_piece_mul[511u - g] : mf_xpow8(len - end);
+                acc ^= mf_gf2_mul(crc, mul);
+            }
+        }
+        acc = mf_warp_xor(acc);
+        if (lane == 0) S.crc_part[warp] = acc;
     }
     MF_PHASE(8);
     __syncthreads();
     MF_PHASE(9);
+    // warp 0: the block header (needs both codes); warps 1..15: bit counts per lane and per segment (need only
+    // the code lengths), so the header's serial latency hides behind the counting
     uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
     if (warp == 0) {
         uint32_t hb = mf_header_warp(S.ll_lens, S.d_lens, outw, S.whdr, lane, phase_clk ? &phase_clk[(size_t)c * 16 + 10] : nullptr);
         if (lane == 0) S.hdr_bits = hb;
+    } else {
+        for (uint32_t seg = warp - 1; seg < MF_SEGS_PER_CHUNK; seg += MF_ENC_WARPS - 1) {
+            const uint32_t base = seg * MF_SEG;
+            uint32_t bits = 0;
+            if (base < len) {
+                const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
+                bits = mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, nullptr);
+            }
+            S.lane_bits[seg][lane] = (uint16_t)bits;
+            uint32_t incl = mf_warp_incl_scan(bits, lane);
+            if (lane == 31) S.seg_bits[seg] = incl;
+        }
     }
     MF_PHASE(13);
     __syncthreads();
-
     MF_PHASE(4);
-    // ---- pass 4: bit counts per lane, per segment
-    for (uint32_t si = 0; si < 2; si++) {
-        const uint32_t seg = warp * 2 + si;
-        const uint32_t base = seg * MF_SEG;
-        uint32_t bits = 0;
-        if (base < len) {
-            const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
-            bits = mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, nullptr);
-        }
-        S.lane_bits[seg][lane] = (uint16_t)bits;
-        uint32_t incl = mf_warp_incl_scan(bits, lane);
-        if (lane == 31) S.seg_bits[seg] = incl;
-    }
-    __syncthreads();
     if (warp == 0) {
         uint32_t b = S.seg_bits[lane];
         uint32_t incl = mf_warp_incl_scan(b, lane);

@@ -32,6 +32,7 @@ struct MfDecChunk {
     uint32_t raw_len;         // 1..32768
     uint32_t hdr_bits;        // MF_STORED_MARK for a stored chunk
     uint32_t blob;
+    const uint8_t *limit;     // end of the packed blob: the bit readers never load past it
 };
 struct MfDecMember {
     uint32_t blob, raw_len, crc_expect, first_chunk, n_chunks;
@@ -110,6 +111,7 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
             d.dst = blob.dst + op + (uint64_t)ch * MF_CHUNK;
             d.raw_len = min((uint32_t)MF_CHUNK, rl - ch * MF_CHUNK);
             d.blob = b;
+            d.limit = src + n;
             chunks[cbase + ch] = d;
             run += d.comp_bytes;
         }
@@ -171,9 +173,9 @@ struct MfLaneWriter {
     __device__ __forceinline__ void put(uint32_t b, const uint32_t (*T)[256]) {
         crc_byte(b, T);
         if (vec) {
-            const uint32_t k = op & 15u;
+            const uint32_t k = op & 15u, bv = b << (8u * (k & 3u)), kj = k >> 2;
 #pragma unroll
-            for (int j = 0; j < 4; j++) if ((int)(k >> 2) == j) w[j] |= b << (8u * (k & 3u));
+            for (int j = 0; j < 4; j++) w[j] |= bv & (0u - (uint32_t)(kj == (uint32_t)j));   // branch-free: w[] stays in registers
             op++;
             if ((op & 15u) == 0) {
                 *reinterpret_cast<uint4 *>(dst + op - 16) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -188,7 +190,8 @@ struct MfLaneWriter {
     __device__ __forceinline__ void spill_window() {
         if (vec) {
             const uint32_t k = op & 15u, base = op - k;
-            for (uint32_t j = 0; j < k; j++) dst[base + j] = (uint8_t)(w[j >> 2] >> (8u * (j & 3u)));
+#pragma unroll
+            for (int j = 0; j < 15; j++) if ((uint32_t)j < k) dst[base + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
             w[0] = w[1] = w[2] = w[3] = 0;
             if (k) vec = false;           // continue with byte stores until the next 16-byte boundary
         }
@@ -209,23 +212,25 @@ struct MfLaneWriter {
 };
 
 struct MfFastReader {
-    const uint32_t *w;
+    const uint32_t *w, *lim;   // next word to fetch; first word that must not be read (end of the blob, rounded up)
     uint64_t buf;
     uint32_t cnt;
-    uint32_t nxt;    // word loaded one refill ahead: its L2 latency hides behind ~32 bits of decoding
-    uint64_t used;   // bits consumed since init
-    __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos) {
+    uint32_t n0, n1;   // words fetched two refills ahead: their L2 latency hides behind ~64 bits of decoding
+    uint64_t used;     // bits consumed since init
+    __device__ __forceinline__ uint32_t fetch() { uint32_t v = (w < lim) ? __ldg(w) : 0u; w++; return v; }
+    __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos, const uint8_t *limit) {
         const uint8_t *a = src + (bitpos >> 3);
         uintptr_t al = (uintptr_t)a & ~(uintptr_t)3;
         uint32_t skip = (uint32_t)((uintptr_t)a - al) * 8u + (uint32_t)(bitpos & 7u);
         w = reinterpret_cast<const uint32_t *>(al);
-        buf = (uint64_t)__ldg(w++) >> skip;
+        lim = reinterpret_cast<const uint32_t *>(((uintptr_t)limit + 3u) & ~(uintptr_t)3);
+        buf = (uint64_t)fetch() >> skip;
         cnt = 32u - skip;
-        buf |= (uint64_t)__ldg(w++) << cnt; cnt += 32u;
-        nxt = __ldg(w++);
+        buf |= (uint64_t)fetch() << cnt; cnt += 32u;
+        n0 = fetch(); n1 = fetch();
         used = 0;
     }
-    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)nxt << cnt; cnt += 32u; nxt = __ldg(w++); } }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)n0 << cnt; cnt += 32u; n0 = n1; n1 = fetch(); } }
     __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }   // k <= 16, call fill() first
     __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; used += k; }
     __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
@@ -365,7 +370,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
             if ((uint64_t)ch.hdr_bits + allbits > (uint64_t)ch.comp_bytes * 8ull) lerr = MF_DEC_E_STREAM;   // index points past the chunk
             else if (seglen) {
                 MfLaneWriter wr; wr.init(ch.dst + seg_base);
-                MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits);
+                MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
                 while (wr.op < seglen) {
                     if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
                     br.fill();
