@@ -189,21 +189,20 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
         // ------------------------------------------------------------------ consumer
         uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
         long long cwait = 0, cstart = dbg ? clock64() : 0;
-        const uint32_t one = one_arg;      // == 1, but only the host knows
+        (void)one_arg;
         for (uint64_t i = 0; i < iters; i++) {
             const int bsel = (int)(i & 1);
             { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_FULL(bsel)); if (dbg) cwait += clock64() - t0_; }
             const uint4 *kwv = reinterpret_cast<const uint4 *>(&S.kw[bsel][lane][0]);
             uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
-            // The integer ALU pipe issues one warp instruction per 2 cycles per SM sub-partition, and a round
-            // needs LOP3 + LEA.HI + SHF there already; the two additions that build T go to the FMA pipe as
-            // IMAD with an opaque multiplier of 1 (ptxas would otherwise fold them back into an ALU IADD3).
+            // (Measured: building T with two FMA-pipe IMADs instead of one ALU IADD3 is slower, 1040 vs 890
+            // cycles per block; the consumer is bound by issued instructions, 4.25 per round this way.)
             // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI).
             // The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the
             // rotate-add and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
 #define MF_RND(F, a, b, c, d, e, kw_) { uint32_t f_ = F(b, c, d); \
-        asm("{\n\t.reg .u32 t_, r_;\n\tmad.lo.u32 t_, %1, %5, %2;\n\tmad.lo.u32 t_, %3, %5, t_;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
-            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a), "r"(one)); \
+        asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
+            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
         b = mf_rol(b, 30); }
 #define MF_RND20(F, q) { \
         uint4 k0 = kwv[5 * (q)], k1 = kwv[5 * (q) + 1], k2 = kwv[5 * (q) + 2], k3 = kwv[5 * (q) + 3], k4 = kwv[5 * (q) + 4]; \
