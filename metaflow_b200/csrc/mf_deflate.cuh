@@ -464,9 +464,18 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
             uint32_t nm = 0;
             uint32_t *ml = S.match[seg];
             uint32_t pos = 0;
+            uint32_t dry = 0;                    // consecutive probed windows that produced no match
             while (pos < seglen) {
                 const uint32_t p = pos + lane;
                 const bool valid = p < seglen;
+                // incompressible stretches (float noise): after 3 dry windows only every 4th window is probed,
+                // the others just feed the literal histogram (LZ4-style acceleration)
+                if (!lz || (dry >= 3 && ((pos >> 5) & 3u) != 0)) {
+                    if (valid) atomicAdd(&S.ll_hist[S.data[base + p]], 1u);
+                    pos += 32;
+                    continue;
+                }
+                const uint32_t nm_before = nm;
                 const uint32_t w = valid ? mf_ld32u(S.data, base + p) : 0u;
                 const bool can = lz && (p + MF_MIN_MATCH <= seglen) && (nm < MF_MAXM);
                 const uint32_t h = (w * 2654435761u) >> (32 - MF_HASH_BITS);
@@ -531,6 +540,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
                 }
                 litmask &= validmask;
                 if ((litmask >> lane) & 1u) atomicAdd(&S.ll_hist[w & 0xFFu], 1u);
+                dry = (nm == nm_before) ? dry + 1 : 0;
                 pos += adv;
             }
             if (lane == 0) S.nmatch[seg] = nm;
