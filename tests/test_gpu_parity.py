@@ -236,6 +236,23 @@ def test_many_small_blobs_dense_sha_mode(gpu_codec):
     assert gpu_codec.hash_batch(blobs[:5000]) == keys[:5000]
 
 
+def test_two_device_context_round_robin():
+    """One context over two GPUs: blob i goes to device i mod 2 (one host thread per device), results come
+    back in input order.  Skipped on a single-GPU box."""
+    from metaflow_b200 import capi
+    from metaflow_b200.codec import GpuCodec
+    if capi.load().mfcas_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(31)
+    blobs = [rng.standard_normal(int(rng.integers(1, 300000)), dtype=np.float32).tobytes() for _ in range(41)] + [b"", b"x"]
+    c = GpuCodec(devices=[0, 1], wave_bytes=8 << 20)
+    try:
+        _roundtrip(c, blobs)
+        assert c.hash_batch(blobs) == [hashlib.sha1(b).hexdigest() for b in blobs]
+    finally:
+        c.close()
+
+
 def test_device_resident_api(gpu_codec):
     import torch
     from metaflow_b200 import capi
