@@ -86,6 +86,31 @@ class ClockSampler(object):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def usable_cores():
+    """Host threads this process may really use: cpu_count, affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]) + 0.5)))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f2:
+                        n = min(n, max(1, int(q / int(f2.read().split()[0]) + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
+
+
 # ----------------------------------------------------------------------------- reference (CPU) arm
 def _cpu_worker(args):
     """One process = one reference task: generate, save through the restated path, load back."""
@@ -123,7 +148,7 @@ def cpu_reference_pass(n_procs, blobs_per_proc, seed0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per = max(1, args.ref_blobs_per_proc)
     for i in range(args.warmup):
         cpu_reference_pass(cores, 1 if i else 1, 7_000_000 + i)
@@ -139,7 +164,7 @@ def run_reference(args, rank, world):
         "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts, save_blobs+load_blobs", "sample": "%d blobs/step (%d procs x %d)" % (cores * per, cores, per),
                    "datastore": "local on tmpfs"},
         "save_GBps": tot_b / tot_s / 1e9, "load_GBps": tot_b / tot_l / 1e9,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
                          "sample": "%d x 16 MiB blobs per step through oracle/ref_path.py (hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files), process per task" % (cores * per)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -334,11 +359,11 @@ def run_ours(args, rank, world, local_rank):
                 traffic = json.load(f).get(names[dominant])
         cpu = None
         if not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
+            cores = usable_cores()
             per = max(1, args.ref_blobs_per_proc)
             cpu_reference_pass(cores, 1, 99)
             b, ts, tl = cpu_reference_pass(cores, per, 5_000_000)
-            cpu = {"value": b / (ts + tl) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            cpu = {"value": b / (ts + tl) / 1e9, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
                    "sample": "%d x 16 MiB blobs (%d procs x %d) through oracle/ref_path.py: hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files" % (cores * per, cores, per),
                    "save_GBps": b / ts / 1e9, "load_GBps": b / tl / 1e9}
         line = {
