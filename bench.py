@@ -399,7 +399,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blobs-per-step", type=int, default=1024)
     ap.add_argument("--wave-mib", type=int, default=2048, help="bytes (in+out) per pipelined wave of the host-pointer API")
-    ap.add_argument("--ref-blobs-per-proc", type=int, default=2)
+    ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
