@@ -328,6 +328,39 @@ def run_ours(args, rank, world, local_rank):
         h2d += n * blob_len + pb; d2h += pb + n * blob_len
     assert h_out[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes() == h_in[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes()
 
+    # ---- L-api: objects -> TaskDataStore.save_artifacts -> files on tmpfs -> load_artifacts -> objects,
+    # pickle and filesystem included; a bounded sample of the same arrays (rank 0 only, informational)
+    api = None
+    if rank == 0 and args.api_blobs > 0:
+        import shutil
+        import tempfile
+        from metaflow_b200 import FlowDataStore, LocalStorage
+        from metaflow_b200.codec import GpuCodec
+        base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+        root = tempfile.mkdtemp(prefix="mfcas_api_", dir=base)
+        codec = GpuCodec(devices=[local_rank], wave_bytes=args.wave_mib << 20)
+        try:
+            arrays = [d_in[i * stride + len(prefix):i * stride + len(prefix) + nbytes].cpu().numpy().view(np.float32).copy() for i in range(args.api_blobs)]
+            fds = FlowDataStore("BenchFlow", storage_impl=LocalStorage, ds_root=root, codec=codec)
+            for attempt in range(2):                       # first pass warms the arenas
+                w = fds.get_task_datastore("1", "work", str(attempt), attempt=0, mode="w")
+                w.init_task()
+                shutil.rmtree(os.path.join(root, "BenchFlow", "data"), ignore_errors=True)
+                t0 = time.perf_counter()
+                w.save_artifacts(((("a%d" % i), a) for i, a in enumerate(arrays)), len_hint=len(arrays))
+                w.done()
+                t1 = time.perf_counter()
+                r = fds.get_task_datastore("1", "work", str(attempt))
+                back = dict(r.load_artifacts(["a%d" % i for i in range(len(arrays))]))
+                t2 = time.perf_counter()
+            assert all(np.array_equal(back["a%d" % i], a) for i, a in enumerate(arrays)), "L-api round trip mismatch"
+            nb = len(arrays) * blob_len
+            api = {"value": nb / (t2 - t0) / 1e9, "unit": UNIT, "save_GBps": nb / (t1 - t0) / 1e9, "load_GBps": nb / (t2 - t1) / 1e9,
+                   "sample": "%d artifacts through TaskDataStore.save_artifacts/load_artifacts, LocalStorage on tmpfs, pickle + files included" % len(arrays)}
+        finally:
+            codec.close()
+            shutil.rmtree(root, ignore_errors=True)
+
     # ---- reduce over ranks (max time), aggregate
     times = torch.tensor([t_save, t_load, e2e_save * 1e3, e2e_load * 1e3] + kms, dtype=torch.float64, device=dev)
     if dist:
@@ -381,6 +414,7 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "save_GBps": total_raw / (e2e_save_ms * 1e-3) / 1e9, "load_GBps": total_raw / (e2e_load_ms * 1e-3) / 1e9,
                     "api": "mfcas_pack_batch + mfcas_unpack_batch on page-locked host buffers"},
+            "api": api,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -401,6 +435,7 @@ def main():
     ap.add_argument("--wave-mib", type=int, default=2048, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--api-blobs", type=int, default=64, help="artifacts in the L-api (objects <-> tmpfs files) sample; 0 = skip")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

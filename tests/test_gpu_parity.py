@@ -236,6 +236,37 @@ def test_many_small_blobs_dense_sha_mode(gpu_codec):
     assert gpu_codec.hash_batch(blobs[:5000]) == keys[:5000]
 
 
+def test_join_fan_in_is_one_batched_unpack(gpu_codec, tmp_path):
+    """BASELINE config C4 shape at reduced size: a join that loads the artifacts of 64 foreach siblings gets
+    them through TaskDataStoreSet's prefetch = ONE batched GPU unpack, on blobs written by us and on blobs
+    written by the reference's code path (gzip level 3, no index)."""
+    from metaflow_b200 import FlowDataStore, LocalStorage, TaskDataStoreSet
+    from metaflow_b200.tuple_util import ForeachFrame
+    rng = np.random.default_rng(41)
+    arrays = [rng.standard_normal(16384, dtype=np.float32) for _ in range(64)]
+    for variant in ("ours", "reference"):
+        root = tmp_path / variant
+        fds = FlowDataStore("JoinFlow", storage_impl=LocalStorage, ds_root=str(root), codec=gpu_codec)
+        for i, a in enumerate(arrays):
+            w = fds.get_task_datastore("1", "leaf", str(100 + i), attempt=0, mode="w")
+            w.init_task()
+            arts = [("x", a), ("_foreach_stack", [ForeachFrame("start", "items", 64, i, i)])]
+            if variant == "ours":
+                w.save_artifacts(iter(arts))
+            else:                                   # blobs as stock Metaflow writes them
+                objects, info = ref_path.save_artifacts(str(root), "JoinFlow", arts)
+                w._objects.update(objects); w._info.update(info)
+            w.done()
+        launches0 = gpu_codec.counters()["kernel_launches"]
+        dss = TaskDataStoreSet(fds, "1", steps=["leaf"], prefetch_data_artifacts=["x", "_foreach_stack"])
+        launches1 = gpu_codec.counters()["kernel_launches"]
+        assert launches1 - launches0 == 4                      # parse + inflate + verify + foreign: one batch
+        got = {ds["_foreach_stack"][0].index: ds["x"] for ds in dss}
+        assert gpu_codec.counters()["kernel_launches"] == launches1   # all served from the prefetch cache
+        assert all(np.array_equal(got[i], a) for i, a in enumerate(arrays))
+        fds.ca_store.set_blob_cache(None)
+
+
 def test_two_device_context_round_robin():
     """One context over two GPUs: blob i goes to device i mod 2 (one host thread per device), results come
     back in input order.  Skipped on a single-GPU box."""
