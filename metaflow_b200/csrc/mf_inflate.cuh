@@ -157,41 +157,42 @@ struct __align__(16) MfDecSmem {
 struct MfLaneWriter {
     uint8_t *dst;        // segment base in global memory
     uint32_t op;         // bytes produced
-    uint32_t w[4];       // the current 16-byte window (valid while `vec`)
-    uint32_t cw, cn;     // CRC: pending word and number of bytes in it
-    uint32_t crc;
-    bool vec;            // window mode possible (dst 16-byte aligned and op at a 16-byte boundary when it started)
-    __device__ __forceinline__ void init(uint8_t *d) { dst = d; op = 0; w[0] = w[1] = w[2] = w[3] = 0; cw = 0; cn = 0; crc = 0; vec = (((uintptr_t)d & 15u) == 0); }
-    __device__ __forceinline__ void crc_byte(uint32_t b, const uint32_t (*T)[256]) {
-        cw |= b << (8u * cn);
-        if (++cn == 4) {
-            uint32_t x = crc ^ cw;
-            crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24];
-            cw = 0; cn = 0;
-        }
+    uint32_t cw;         // the 4-byte word being assembled: bytes [op & ~3, op)
+    uint32_t w[4];       // completed words of the current 16-byte window (window mode)
+    uint32_t crc;        // raw CRC-32 of the completed words
+    bool vec;            // window mode: bytes reach memory 16 at a time; otherwise byte by byte
+    bool aligned;        // dst is 16-byte aligned (window mode possible at all)
+    __device__ __forceinline__ void init(uint8_t *d) {
+        dst = d; op = 0; cw = 0; w[0] = w[1] = w[2] = w[3] = 0; crc = 0;
+        aligned = (((uintptr_t)d & 15u) == 0); vec = aligned;
     }
-    __device__ __forceinline__ void put(uint32_t b, const uint32_t (*T)[256]) {
-        crc_byte(b, T);
+    __device__ __forceinline__ void word_done(const uint32_t (*T)[256]) {     // op is a multiple of 4 now
+        const uint32_t x = crc ^ cw;
+        crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24];
         if (vec) {
-            const uint32_t k = op & 15u, bv = b << (8u * (k & 3u)), kj = k >> 2;
+            const uint32_t j = ((op - 4u) >> 2) & 3u;
 #pragma unroll
-            for (int j = 0; j < 4; j++) w[j] |= bv & (0u - (uint32_t)(kj == (uint32_t)j));   // branch-free: w[] stays in registers
-            op++;
+            for (int k = 0; k < 4; k++) w[k] |= cw & (0u - (uint32_t)(j == (uint32_t)k));    // branch-free: w[] stays in registers
             if ((op & 15u) == 0) {
                 *reinterpret_cast<uint4 *>(dst + op - 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 w[0] = w[1] = w[2] = w[3] = 0;
             }
-        } else {
-            dst[op++] = (uint8_t)b;
-            if ((op & 15u) == 0 && (((uintptr_t)dst & 15u) == 0)) vec = true;      // realigned: back to window mode
-        }
+        } else if ((op & 15u) == 0 && aligned) vec = true;                    // realigned: back to window mode
+        cw = 0;
     }
-    // bytes of the open window reach memory (needed before a match reads them back, and at the end)
+    __device__ __forceinline__ void put(uint32_t b, const uint32_t (*T)[256]) {
+        if (!vec) dst[op] = (uint8_t)b;
+        cw |= b << (8u * (op & 3u));
+        op++;
+        if ((op & 3u) == 0) word_done(T);
+    }
+    // bytes still held in registers reach memory (before a match reads them back, and at the end)
     __device__ __forceinline__ void spill_window() {
         if (vec) {
             const uint32_t k = op & 15u, base = op - k;
 #pragma unroll
-            for (int j = 0; j < 15; j++) if ((uint32_t)j < k) dst[base + j] = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+            for (int j = 0; j < 15; j++)
+                if ((uint32_t)j < k) dst[base + j] = (uint8_t)((((uint32_t)j >> 2) < (k >> 2) ? w[j >> 2] : cw) >> (8 * (j & 3)));
             w[0] = w[1] = w[2] = w[3] = 0;
             if (k) vec = false;           // continue with byte stores until the next 16-byte boundary
         }
@@ -199,14 +200,17 @@ struct MfLaneWriter {
     __device__ __forceinline__ void copy_match(uint32_t len, uint32_t dist, const uint32_t (*T)[256]) {
         spill_window();
         vec = false;                      // the source may be the bytes just written: everything goes through memory
-        for (uint32_t k = 0; k < len; k++) { uint32_t b = dst[op - dist]; crc_byte(b, T); dst[op++] = (uint8_t)b; }
-        if ((op & 15u) == 0 && (((uintptr_t)dst & 15u) == 0)) vec = true;
+        for (uint32_t k = 0; k < len; k++) {
+            const uint32_t b = dst[op - dist];
+            dst[op] = (uint8_t)b;
+            cw |= b << (8u * (op & 3u));
+            op++;
+            if ((op & 3u) == 0) word_done(T);
+        }
     }
     __device__ __forceinline__ uint32_t finish(const uint32_t (*T)[256]) {
         spill_window();
-        // CRC tail: fewer than 4 pending bytes
-        for (uint32_t j = 0; j < cn; j++) crc = T[0][(crc ^ (cw >> (8u * j))) & 0xFFu] ^ (crc >> 8);
-        cn = 0;
+        for (uint32_t j = 0; j < (op & 3u); j++) crc = T[0][(crc ^ (cw >> (8u * j))) & 0xFFu] ^ (crc >> 8);   // CRC tail
         return crc;
     }
 };
