@@ -6,6 +6,7 @@ _unpack_v1) with mfcas_pack_batch / mfcas_hash_batch / mfcas_unpack_batch on the
 Blobs are packed into page-locked arenas so every wave moves with one cudaMemcpyAsync each way.
 """
 import ctypes
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -119,11 +120,19 @@ class GpuCodec(object):
             total += _align(int(lens[i])) + _ALIGN
         self._in.ensure(total + _ALIGN)
         arr = self._in.arr
-        for i, b in enumerate(blobs):
+
+        def stage(i):
             ln = int(lens[i])
             if ln:
                 o = int(offs[i])
-                arr[o:o + ln] = _as_u8(b)
+                arr[o:o + ln] = _as_u8(blobs[i])       # numpy releases the GIL for large copies
+
+        if n >= 4 and total >= (64 << 20):
+            with ThreadPoolExecutor(max_workers=8) as pool:
+                list(pool.map(stage, range(n)))
+        else:
+            for i in range(n):
+                stage(i)
         src = (offs + np.uint64(self._in.base)).astype(np.uint64)
         return lens, src
 

@@ -10,6 +10,7 @@ What changes is HOW: the reference hashes and gzips one blob at a time on one CP
 iterator is drained in windows, and each window goes through GpuCodec.pack_batch /
 unpack_batch (SHA-1, DEFLATE, CRC-32, INFLATE on the GPUs, sharded round-robin across devices).
 """
+import os
 from collections import namedtuple
 from io import BytesIO
 
@@ -122,48 +123,65 @@ class ContentAddressedStore(object):
         if not pending:
             return
         per_blob_unpack = "_unpack_v1" in self.__dict__ or type(self)._unpack_v1 is not ContentAddressedStore._unpack_v1
+        read_files = getattr(storage, "read_files", None)
         with storage.load_bytes(pending) as loaded:
-            batch, batch_bytes = [], 0
+            window, window_bytes = [], 0          # (key, path_key, meta, file_path) of blobs to decode on the GPU
             for path_key, file_path, meta in loaded:
                 key = storage.path_split(path_key)[-1]
-                with open(file_path, "rb") as f:
-                    if force_raw or (meta and meta.get("cas_raw", False)):
+                if force_raw or (meta and meta.get("cas_raw", False)):
+                    with open(file_path, "rb") as f:
                         blob = f.read()
-                        if self._blob_cache:
-                            self._blob_cache.store_key(key, blob)
-                        yield (key, blob, meta) if is_transfer else (key, blob)
-                        continue
-                    if meta is None:
-                        unpack_code = self._unpack_backward_compatible  # pre-meta datastores
-                        version = 1
-                    else:
-                        version = meta.get("cas_version", -1)
-                        if version == -1:
-                            raise DataException("Could not extract encoding version for '%s'" % path_key)
-                        unpack_code = getattr(self, "_unpack_v%d" % version, None)
-                        if unpack_code is None:
-                            raise DataException(
-                                "Unknown encoding version %d for '%s' -- the artifact is either corrupt or you "
-                                "need to update Metaflow to the latest version" % (version, path_key)
-                            )
-                    if per_blob_unpack or version != 1:
+                    if self._blob_cache:
+                        self._blob_cache.store_key(key, blob)
+                    yield (key, blob, meta) if is_transfer else (key, blob)
+                    continue
+                if meta is None:
+                    unpack_code = self._unpack_backward_compatible  # pre-meta datastores
+                    version = 1
+                else:
+                    version = meta.get("cas_version", -1)
+                    if version == -1:
+                        raise DataException("Could not extract encoding version for '%s'" % path_key)
+                    unpack_code = getattr(self, "_unpack_v%d" % version, None)
+                    if unpack_code is None:
+                        raise DataException(
+                            "Unknown encoding version %d for '%s' -- the artifact is either corrupt or you "
+                            "need to update Metaflow to the latest version" % (version, path_key)
+                        )
+                if per_blob_unpack or version != 1:
+                    with open(file_path, "rb") as f:
                         try:
                             blob = unpack_code(f)
                         except Exception as e:
                             raise DataException("Could not unpack artifact '%s': %s" % (path_key, e))
-                        if self._blob_cache:
-                            self._blob_cache.store_key(key, blob)
-                        yield (key, blob, meta) if is_transfer else (key, blob)
-                        continue
-                    packed = f.read()
-                batch.append((key, path_key, meta, packed))
-                batch_bytes += len(packed)
-                if batch_bytes >= self._window_bytes:
-                    for out in self._flush_unpack(batch, is_transfer, as_bytes):
+                    if self._blob_cache:
+                        self._blob_cache.store_key(key, blob)
+                    yield (key, blob, meta) if is_transfer else (key, blob)
+                    continue
+                window.append((key, path_key, meta, file_path))
+                window_bytes += os.path.getsize(file_path)
+                if window_bytes >= self._window_bytes:
+                    for out in self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes):
                         yield out
-                    batch, batch_bytes = [], 0
-            for out in self._flush_unpack(batch, is_transfer, as_bytes):
+                    window, window_bytes = [], 0
+            for out in self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes):
                 yield out
+
+    @staticmethod
+    def _read_window(window, read_files):
+        """-> [(key, path_key, meta, packed bytes)]; the files of a window are read in parallel when the
+        storage backend offers it."""
+        if not window:
+            return []
+        paths = [w[3] for w in window]
+        if read_files is not None:
+            datas = read_files(paths)
+        else:
+            datas = []
+            for p in paths:
+                with open(p, "rb") as f:
+                    datas.append(f.read())
+        return [(k, pk, m, d) for (k, pk, m, _), d in zip(window, datas)]
 
     def _flush_unpack(self, batch, is_transfer, as_bytes):
         if not batch:
