@@ -291,41 +291,70 @@ def run_ours(args, rank, world, local_rank):
     verify([1])
     raw_bytes = args.steps * n * blob_len
 
-    # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies timed)
-    h_in_p = lib.mfcas_alloc_pinned(B * stride); h_pk_p = lib.mfcas_alloc_pinned(B * cstride); h_out_p = lib.mfcas_alloc_pinned(B * stride)
+    # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies timed).
+    # Save = mfcas_pack_batch_extents (the call GpuCodec.pack_batch makes: 2 MiB stripes, every stripe its own
+    # gzip member in a fixed slot; a writer writev()s the extents into the CAS file).  Between the timed save and
+    # the timed load the extents are made contiguous on the host -- that is the file write of the real path and is
+    # not timed here -- and load = mfcas_unpack_batch on whole packed blobs.
+    ecount = lib.mfcas_pack_extent_count(blob_len)
+    ecap = lib.mfcas_pack_extent_bound(blob_len)
+    estride = (ecap + 255) // 256 * 256 + 256
+    h_in_p = lib.mfcas_alloc_pinned(B * stride); h_pk_p = lib.mfcas_alloc_pinned(B * estride); h_out_p = lib.mfcas_alloc_pinned(B * stride)
     assert h_in_p and h_pk_p and h_out_p, "pinned allocation failed"
     h_in = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_in_p))
     h_out = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_out_p))
-    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (B * cstride)).from_address(h_pk_p))
+    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (B * estride)).from_address(h_pk_p))
     hsrc = (vp * n)(*[h_in_p + i * stride for i in range(n)])
-    hpk = (vp * n)(*[h_pk_p + i * cstride for i in range(n)])
+    hpk = (vp * n)(*[h_pk_p + i * estride for i in range(n)])
     hout = (vp * n)(*[h_out_p + i * stride for i in range(n)])
+    epcap = (u64 * n)(*([ecap] * n))
+    ext_off = (u64 * (n * ecount))()
+    ext_len = (u64 * (n * ecount))()
     t_in = torch.from_numpy(h_in)
     e2e_save = e2e_load = 0.0
     e2e_steps = args.steps
     h2d = d2h = 0
 
-    def step_host():
+    def save_host():
         t0 = time.perf_counter()
-        check(lib.mfcas_pack_batch(ctx, n, hsrc, slen, hpk, pcap, plen, sha, st), "pack_batch")
-        t1 = time.perf_counter()
-        check(lib.mfcas_unpack_batch(ctx, n, hpk, plen, hout, ocap, olen, st), "unpack_batch")
-        t2 = time.perf_counter()
-        return t1 - t0, t2 - t1
+        check(lib.mfcas_pack_batch_extents(ctx, n, hsrc, slen, hpk, epcap, ext_off, ext_len, sha, st), "pack_batch_extents")
+        return time.perf_counter() - t0
 
-    generate(20_000); t_in.copy_(d_in); torch.cuda.synchronize(); step_host()       # warm-up (arena allocation)
+    def compact_host():
+        """extents -> contiguous packed blob at the start of its slot (what writev into the CAS file does)"""
+        eo = np.frombuffer(ext_off, dtype=np.uint64).reshape(n, ecount)
+        el = np.frombuffer(ext_len, dtype=np.uint64).reshape(n, ecount)
+        for i in range(n):
+            base, cur = i * estride, int(el[i, 0])
+            for k in range(1, ecount):
+                o, ln = int(eo[i, k]), int(el[i, k])
+                h_pk[base + cur:base + cur + ln] = h_pk[base + o:base + o + ln]
+                cur += ln
+            plen[i] = cur
+
+    def load_host():
+        t0 = time.perf_counter()
+        check(lib.mfcas_unpack_batch(ctx, n, hpk, plen, hout, ocap, olen, st), "unpack_batch")
+        return time.perf_counter() - t0
+
+    generate(20_000); t_in.copy_(d_in); torch.cuda.synchronize(); save_host(); compact_host(); load_host()       # warm-up (arena allocation)
+    import gzip
     import hashlib
     blob0 = h_in[:blob_len].tobytes()
     assert sha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
+    assert gzip.decompress(h_pk[:plen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"
     barrier()
     for s in range(e2e_steps):
         generate(30_000 + s)
         t_in.copy_(d_in)                     # device -> page-locked host buffer (untimed: it only refreshes the inputs)
         barrier()
-        a, b = step_host()
+        a = save_host()
+        compact_host()
+        barrier()
+        b = load_host()
         e2e_save += a; e2e_load += b
         pb = sum(plen)
-        h2d += n * blob_len + pb; d2h += pb + n * blob_len
+        h2d += n * blob_len + pb; d2h += n * ecap + n * blob_len
     assert h_out[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes() == h_in[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes()
 
     # ---- L-api (SURVEY 8d): objects -> TaskDataStore.save_artifacts -> files on tmpfs -> load_artifacts -> objects,
@@ -413,7 +442,7 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "save_GBps": total_raw / (e2e_save_ms * 1e-3) / 1e9, "load_GBps": total_raw / (e2e_load_ms * 1e-3) / 1e9,
-                    "api": "mfcas_pack_batch + mfcas_unpack_batch on page-locked host buffers"},
+                    "api": "mfcas_pack_batch_extents + mfcas_unpack_batch on page-locked host buffers"},
             "api": api,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -432,7 +461,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--blobs-per-step", type=int, default=1024)
-    ap.add_argument("--wave-mib", type=int, default=2048, help="bytes (in+out) per pipelined wave of the host-pointer API")
+    ap.add_argument("--wave-mib", type=int, default=4096, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--api-blobs", type=int, default=64, help="artifacts in the L-api (objects <-> tmpfs files) sample; 0 = skip")

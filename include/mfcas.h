@@ -75,6 +75,22 @@ int mfcas_pack_batch(mfcas_ctx *ctx, uint64_t n,
                      void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len,
                      uint8_t *sha1, int32_t *status);
 
+/* Striped form of mfcas_pack_batch for large blobs.  Every 2 MiB stripe of a blob becomes its own gzip
+ * member, written at a fixed slot of dst[i]; the packed blob is the concatenation, in order, of the
+ * extents dst[i][ext_off[k] .. ext_off[k] + ext_len[k]) for k = base_i .. base_i + count_i - 1, where
+ * count_i = mfcas_pack_extent_count(src_len[i]) and base_i is the sum of the counts of blobs 0..i-1
+ * (ext_off / ext_len hold the sum of all counts entries).  dst_cap[i] >= mfcas_pack_extent_bound(src_len[i]).
+ * The waves go stripe by stripe across all blobs and the SHA-1 state is carried between them, so hashing,
+ * encoding and the copy back overlap the upload instead of trailing the last blob (a writer simply
+ * writev()s the extents).  Same digests, same decoded bytes as mfcas_pack_batch. */
+uint64_t mfcas_pack_extent_count(uint64_t src_len);
+uint64_t mfcas_pack_extent_bound(uint64_t src_len);
+int mfcas_pack_batch_extents(mfcas_ctx *ctx, uint64_t n,
+                             const void *const *src, const uint64_t *src_len,
+                             void *const *dst, const uint64_t *dst_cap,
+                             uint64_t *ext_off, uint64_t *ext_len,
+                             uint8_t *sha1, int32_t *status);
+
 /* key only: replaces sha1() for raw blobs (save_blobs(raw=True), flow_datastore.py:348-367)
  * and for dedup-before-pack (content_addressed_store.py:107). */
 int mfcas_hash_batch(mfcas_ctx *ctx, uint64_t n,

@@ -40,6 +40,9 @@ SIGNATURES = [
     ("mfcas_free_pinned", None, [ctypes.c_void_p]),
     ("mfcas_pack_bound", ctypes.c_uint64, [ctypes.c_uint64]),
     ("mfcas_pack_batch", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, ctypes.c_void_p, _i32p]),
+    ("mfcas_pack_extent_count", ctypes.c_uint64, [ctypes.c_uint64]),
+    ("mfcas_pack_extent_bound", ctypes.c_uint64, [ctypes.c_uint64]),
+    ("mfcas_pack_batch_extents", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, _u64p, ctypes.c_void_p, _i32p]),
     ("mfcas_hash_batch", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _vpp, _u64p, ctypes.c_void_p, _i32p]),
     ("mfcas_unpacked_size", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _u64p, ctypes.POINTER(ctypes.c_int)]),
     ("mfcas_unpack_batch", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, _i32p]),

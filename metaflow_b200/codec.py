@@ -60,6 +60,26 @@ def _as_u8(blob):
     return np.frombuffer(blob, dtype=np.uint8)
 
 
+class Packed(object):
+    """The RFC 1952 bytes of one packed blob as one or more views over the page-locked output arena
+    (several when the blob was packed in stripes: the file is their concatenation -- writers writev them).
+    Valid until the next pack/unpack call of the codec that produced it."""
+
+    __slots__ = ("views",)
+
+    def __init__(self, views):
+        self.views = views
+
+    def __len__(self):
+        return sum(len(v) for v in self.views)
+
+    def __bytes__(self):
+        return bytes(self.views[0]) if len(self.views) == 1 else b"".join(bytes(v) for v in self.views)
+
+    def tobytes(self):
+        return bytes(self)
+
+
 class UnpackError(Exception):
     """Per-blob decode failure; str() mirrors the message the reference's gzip reader gives."""
 
@@ -159,8 +179,47 @@ class GpuCodec(object):
         return [raw[20 * i:20 * i + 20].hex() for i in range(n)]
 
     def pack_batch(self, blobs):
-        """-> (keys, packed) where packed[i] is a memoryview over page-locked memory holding the
-        RFC 1952 bytes of blob i.  The views stay valid until the next pack/unpack call."""
+        """-> (keys, packed): packed[i] is a `Packed` (views over page-locked memory holding the RFC 1952
+        bytes of blob i, one view per 2 MiB stripe).  Valid until the next pack/unpack call.
+        Uses mfcas_pack_batch_extents: stripes of all blobs are uploaded, hashed, encoded and copied back
+        wave by wave, so nothing trails the last blob."""
+        n = len(blobs)
+        if n == 0:
+            return [], []
+        lib = self._lib
+        lens, src = self._stage_inputs(blobs)
+        counts = np.fromiter((lib.mfcas_pack_extent_count(int(x)) for x in lens), dtype=np.uint64, count=n)
+        caps = np.fromiter((lib.mfcas_pack_extent_bound(int(x)) for x in lens), dtype=np.uint64, count=n)
+        ooffs = np.zeros(n, dtype=np.uint64)
+        total = 0
+        for i in range(n):
+            ooffs[i] = total
+            total += _align(int(caps[i])) + _ALIGN
+        self._out.ensure(total + _ALIGN)
+        dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
+        bases = np.concatenate(([0], np.cumsum(counts)[:-1])).astype(np.int64)
+        n_ext = int(counts.sum())
+        ext_off = np.zeros(n_ext, dtype=np.uint64)
+        ext_len = np.zeros(n_ext, dtype=np.uint64)
+        sha = np.empty(20 * n, dtype=np.uint8)
+        st = np.zeros(n, dtype=np.int32)
+        self._check(lib.mfcas_pack_batch_extents(self._ctx, n, self._pp(src), self._p64(lens), self._pp(dst), self._p64(caps),
+                                                 self._p64(ext_off), self._p64(ext_len), sha.ctypes.data,
+                                                 st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        if st.any():
+            bad = int(np.flatnonzero(st)[0])
+            raise DataException("GPU pack failed for blob %d: %s" % (bad, capi.STATUS_TEXT.get(int(st[bad]), st[bad])))
+        raw = sha.tobytes()
+        keys = [raw[20 * i:20 * i + 20].hex() for i in range(n)]
+        mv = memoryview(self._out.arr)
+        packed = []
+        for i in range(n):
+            o, b = int(ooffs[i]), int(bases[i])
+            packed.append(Packed([mv[o + int(ext_off[b + k]):o + int(ext_off[b + k]) + int(ext_len[b + k])] for k in range(int(counts[i]))]))
+        return keys, packed
+
+    def pack_batch_contiguous(self, blobs):
+        """Same result through mfcas_pack_batch: one contiguous view per blob (blob-granular waves)."""
         n = len(blobs)
         if n == 0:
             return [], []
@@ -184,8 +243,7 @@ class GpuCodec(object):
         raw = sha.tobytes()
         keys = [raw[20 * i:20 * i + 20].hex() for i in range(n)]
         mv = memoryview(self._out.arr)
-        packed = [mv[int(ooffs[i]):int(ooffs[i]) + int(dlen[i])] for i in range(n)]
-        return keys, packed
+        return keys, [Packed([mv[int(ooffs[i]):int(ooffs[i]) + int(dlen[i])]]) for i in range(n)]
 
     # ------------------------------------------------------------------ load side
     def unpacked_size(self, packed):

@@ -20,11 +20,15 @@
 #include <cuda_runtime.h>
 
 struct MfHashDesc {
-    const uint8_t *src;   // device pointer, 16-byte aligned
-    uint64_t len;
-    uint32_t out_index;   // where the digest goes: digests + 20 * out_index
-    uint32_t pad;
+    const uint8_t *src;   // device pointer, 16-byte aligned: the bytes to hash in THIS launch
+    uint64_t len;         // their count; a multiple of 64 unless this is the last piece of the message
+    uint32_t out_index;   // where the digest goes (last piece): digests + 20 * out_index
+    uint32_t flags;       // MF_SHA_FIRST: start from the initial state; MF_SHA_LAST: pad and emit the digest
+    uint64_t total_len;   // length of the whole message (for the padding of the last piece)
+    uint32_t *state;      // 5 words carried between the pieces of one message (may be null when FIRST|LAST)
 };
+#define MF_SHA_FIRST 1u
+#define MF_SHA_LAST 2u
 
 __device__ __forceinline__ uint32_t mf_rol(uint32_t x, int s) { return __funnelshift_l(x, x, s); }
 __device__ __forceinline__ uint32_t mf_bswap(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -102,7 +106,10 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
     const uint64_t len = valid ? blobs[s].len : 0;
     const uint64_t nfull = len >> 6;
     const uint32_t r = (uint32_t)(len & 63u);
-    const uint64_t nb = valid ? nfull + (r < 56 ? 1 : 2) : 0;       // blocks incl. padding
+    const uint32_t sflags = valid ? blobs[s].flags : (MF_SHA_FIRST | MF_SHA_LAST);
+    const bool is_last = (sflags & MF_SHA_LAST) != 0;
+    // blocks to run in this launch: the full blocks of the piece, plus the padding block(s) on the last piece
+    const uint64_t nb = valid ? (is_last ? nfull + (r < 56 ? 1 : 2) : nfull) : 0;
     uint64_t iters = nb;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, iters, d); iters = o > iters ? o : iters; }
@@ -140,7 +147,7 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
         };
         issue_group(0);
         issue_group(1);
-        const uint64_t bits = len << 3;
+        const uint64_t bits = (valid ? blobs[s].total_len : 0) << 3;
         long long pwait = 0, pstart = dbg ? clock64() : 0;
         const int b = (int)pid;
         uint64_t cur_group = ~0ull;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
                 w[8] = mf_bswap(v2.x); w[9] = mf_bswap(v2.y); w[10] = mf_bswap(v2.z); w[11] = mf_bswap(v2.w);
                 w[12] = mf_bswap(v3.x); w[13] = mf_bswap(v3.y); w[14] = mf_bswap(v3.z); w[15] = mf_bswap(v3.w);
             }
-            if (i >= nfull) {
+            if (is_last && i >= nfull) {
                 // padding: bytes past the message are zero in the staging row already (cp.async zero-fill)
                 if (i == nfull) {
                     const uint32_t marker = 0x80u << (24 - 8 * (r & 3)), rk = r >> 2;
@@ -188,6 +195,10 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
     } else {
         // ------------------------------------------------------------------ consumer
         uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
+        if (valid && !(sflags & MF_SHA_FIRST)) {               // continue a message hashed piecewise (striped upload)
+            const uint32_t *st = blobs[s].state;
+            h0 = st[0]; h1 = st[1]; h2 = st[2]; h3 = st[3]; h4 = st[4];
+        }
         long long cwait = 0, cstart = dbg ? clock64() : 0;
         (void)one_arg;
         for (uint64_t i = 0; i < iters; i++) {
@@ -220,7 +231,11 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
             if (i + 2 < iters) mf_bar_arrive(MF_BAR_EMPTY(bsel));
         }
         if (dbg && lane == 0) { dbg[blockIdx.x * 4 + 2] = (unsigned long long)cwait; dbg[blockIdx.x * 4 + 3] = (unsigned long long)(clock64() - cstart); }
-        if (valid) {
+        if (valid && !is_last) {
+            uint32_t *st = blobs[s].state;
+            st[0] = h0; st[1] = h1; st[2] = h2; st[3] = h3; st[4] = h4;
+        }
+        if (valid && is_last) {
             uint8_t *out = digests + 20ull * blobs[s].out_index;
             const uint32_t hh[5] = {h0, h1, h2, h3, h4};
 #pragma unroll

@@ -86,6 +86,8 @@ struct WaveCtx {
 struct DeviceState {
     int dev = -1;
     cudaStream_t compute = nullptr;      // all chunk-parallel encode kernels of all waves, in submission order
+    cudaStream_t sha_chain = nullptr;    // striped packing: the SHA-1 pieces of all waves, in order (state is carried)
+    DevBuf sha_state;                    // 5 words per blob of the running striped call
     std::vector<WaveCtx> ring;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -124,7 +126,7 @@ struct Carver {
     size_t take(size_t bytes, size_t align = 256) { off = align_up(off, align); size_t o = off; off += bytes; return o; }
 };
 
-#define MF_RING 12
+#define MF_RING 8
 // encoder CTAs resident at once: 2 per SM x 148 SMs minus 24, i.e. ~24 SMs keep one free 100+ KB slot for SHA-1 CTAs
 #define MF_ENC_GRID_CAP 272u
 
@@ -146,6 +148,7 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
 int device_setup(DeviceState &D) {
     CU(cudaSetDevice(D.dev));
     CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
+    { int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CU(cudaStreamCreateWithPriority(&D.sha_chain, cudaStreamNonBlocking, hi)); }
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
     CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -172,6 +175,8 @@ void device_teardown(DeviceState &D) {
     }
     D.ring.clear();
     if (D.compute) { cudaStreamSynchronize(D.compute); cudaStreamDestroy(D.compute); D.compute = nullptr; }
+    if (D.sha_chain) { cudaStreamSynchronize(D.sha_chain); cudaStreamDestroy(D.sha_chain); D.sha_chain = nullptr; }
+    D.sha_state.release();
 }
 
 // Copies a set of (host ptr, device ptr, len) with runs of contiguous pairs merged into one memcpy.
@@ -198,8 +203,11 @@ static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMIN
 // small result block (dst_len, status, digests) to pinned host memory; W.ev_res fires when that is there.
 // `upload` (host-pointer API): the wave's input copies; they are enqueued AFTER the small descriptor copy so
 // that nothing small ever queues behind other waves' gigabyte copies on the copy engine.
+// `chain` (striped packing): SHA-1 descriptors of message PIECES (state carried across waves), hashed on
+// D.sha_chain so that the pieces of one blob run in order.
 int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                void *const *d_dst, const uint64_t *dst_cap, bool want_pack, const CopyPlan *upload) {
+                void *const *d_dst, const uint64_t *dst_cap, bool want_pack, const CopyPlan *upload,
+                const MfHashDesc *chain = nullptr) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
@@ -218,7 +226,9 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
     MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
     uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
-    {   // SHA-1 streams sorted by length (descending): the 32 streams of a CTA then finish together
+    if (chain) {
+        memcpy(h_hash, chain, sizeof(MfHashDesc) * n);
+    } else {   // SHA-1 streams sorted by length (descending): the 32 streams of a CTA then finish together
         std::vector<uint32_t> order(n);
         for (uint64_t i = 0; i < n; i++) order[i] = (uint32_t)i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return src_len[a] > src_len[b]; });
@@ -227,7 +237,9 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             h_hash[k].src = static_cast<const uint8_t *>(d_src[i]);
             h_hash[k].len = src_len[i];
             h_hash[k].out_index = i;
-            h_hash[k].pad = 0;
+            h_hash[k].flags = MF_SHA_FIRST | MF_SHA_LAST;
+            h_hash[k].total_len = src_len[i];
+            h_hash[k].state = nullptr;
         }
     }
     uint32_t mi = 0, ci = 0;
@@ -271,7 +283,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     uint8_t *dw = W.d_work.as<uint8_t>();
     uint8_t *dd = W.d_desc.as<uint8_t>();
     uint8_t *dres = dw + o_res;
-    cudaStream_t s = W.stream, s2 = W.stream2;
+    cudaStream_t s = W.stream, s2 = chain ? D.sha_chain : W.stream2;
     unsigned long long *phase = nullptr;      // MFCAS_PHASE_TIMING=1: per-chunk clock64 at phase boundaries
     if (phase_timing_on() && want_pack && n_chunks) {
         CU(W.phase.ensure(n_chunks * 16 * sizeof(unsigned long long)));
@@ -582,6 +594,124 @@ int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
     return rc;
 }
 
+// ------------------------------------------------------------------ striped packing (extent output)
+// A blob is cut into 2 MiB stripes; every stripe becomes its own gzip member in a fixed slot of the blob's
+// destination buffer, and the waves go stripe-major (stripe 0 of every blob, then stripe 1, ...).  The SHA-1
+// of a blob is hashed piecewise (state carried on D.sha_chain), so it progresses while later stripes are still
+// on the PCIe bus, and every wave's output goes back as soon as it is encoded.  The packed blob is the
+// concatenation of its extents -- a valid multi-member RFC 1952 file.
+#define MF_STRIPE_CHUNKS 64u
+inline uint64_t stripe_raw() { return (uint64_t)MF_STRIPE_CHUNKS * MF_CHUNK; }
+inline uint64_t ext_count(uint64_t len) { return len == 0 ? 1 : (len + stripe_raw() - 1) / stripe_raw(); }
+inline uint64_t ext_slot() { return align_up(mf_pack_bound(stripe_raw()), 256); }
+inline uint64_t ext_bound(uint64_t len) {
+    const uint64_t c = ext_count(len);
+    return (c - 1) * ext_slot() + mf_pack_bound(len - (c - 1) * stripe_raw());
+}
+
+struct ExtIO {
+    const Shard *sh;
+    const void *const *src; const uint64_t *src_len; void *const *dst; const uint64_t *dst_cap;
+    const uint64_t *ext_base;        // index of blob i's first extent in ext_off / ext_len
+    uint64_t *ext_off, *ext_len; uint8_t *sha1; int32_t *status;
+};
+struct ExtUnit { uint64_t blob; uint32_t m; uint32_t sblob; };
+
+int ext_wave_finish(DeviceState &D, WaveCtx &W, const ExtIO &io, const std::vector<ExtUnit> &units) {
+    int rc = pack_collect(D, W, W.w_dlen.data(), W.w_sha.data(), W.w_st.data());
+    if (rc != MFCAS_OK) return rc;
+    CU(cudaEventSynchronize(W.ev_done));
+    for (size_t k = 0; k < W.wn; k++) {
+        const ExtUnit &u = units[W.pos + k];
+        io.ext_len[io.ext_base[u.blob] + u.m] = W.w_dlen[k];
+        if (W.w_st[k] != 0 && io.status[u.blob] == 0) io.status[u.blob] = W.w_st[k];
+        if (u.m + 1 == ext_count(io.src_len[u.blob])) memcpy(io.sha1 + 20 * u.blob, W.w_sha.data() + 20 * k, 20);
+    }
+    W.state = 0;
+    return MFCAS_OK;
+}
+
+int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
+    const Shard &sh = *io.sh;
+    CU(cudaSetDevice(D.dev));
+    // units in stripe-major order; blobs whose destination is too small are reported and left out
+    std::vector<ExtUnit> units;
+    uint64_t maxc = 0;
+    std::vector<uint8_t> skip(sh.idx.size(), 0);
+    for (size_t j = 0; j < sh.idx.size(); j++) {
+        const uint64_t i = sh.idx[j];
+        io.status[i] = 0;
+        const uint64_t c = ext_count(io.src_len[i]);
+        for (uint64_t m = 0; m < c; m++) { io.ext_off[io.ext_base[i] + m] = m * ext_slot(); io.ext_len[io.ext_base[i] + m] = 0; }
+        if (io.dst_cap[i] < ext_bound(io.src_len[i])) { io.status[i] = MFCAS_E_DST_TOO_SMALL; skip[j] = 1; continue; }
+        maxc = std::max(maxc, c);
+    }
+    for (uint64_t m = 0; m < maxc; m++)
+        for (size_t j = 0; j < sh.idx.size(); j++)
+            if (!skip[j] && m < ext_count(io.src_len[sh.idx[j]])) units.push_back({sh.idx[j], (uint32_t)m, (uint32_t)j});
+    CU(D.sha_state.ensure(sh.idx.size() * 5 * sizeof(uint32_t) + 64));
+    uint32_t *d_state = D.sha_state.as<uint32_t>();
+    const uint64_t wave_bytes = ctx->wave_bytes;
+    std::vector<MfHashDesc> chain;
+    size_t pos = 0, w = 0;
+    int rc = MFCAS_OK;
+    while (pos < units.size() && rc == MFCAS_OK) {
+        size_t end = pos; uint64_t in_bytes = 0, out_bytes = 0;
+        std::vector<uint64_t> ioff, ooff, caps, lens;
+        while (end < units.size()) {
+            const ExtUnit &u = units[end];
+            const uint64_t off = (uint64_t)u.m * stripe_raw();
+            const uint64_t len = std::min<uint64_t>(stripe_raw(), io.src_len[u.blob] - off);
+            const uint64_t il = align_up(len, 256) + 256, oc = mf_pack_bound(len), ol = align_up(oc, 256) + 256;
+            if (end > pos && in_bytes + il + out_bytes + ol > wave_bytes) break;
+            ioff.push_back(in_bytes); ooff.push_back(out_bytes); caps.push_back(oc); lens.push_back(len);
+            in_bytes += il; out_bytes += ol; end++;
+        }
+        const size_t wn = end - pos;
+        WaveCtx &W = D.ring[w % D.ring.size()];
+        if (W.state == 1) rc = ext_wave_finish(D, W, io, units);
+        if (rc != MFCAS_OK) break;
+        CU(W.in_arena.ensure(in_bytes + 256));
+        CU(W.out_arena.ensure(out_bytes + 256));
+        CopyPlan up;
+        W.w_src.resize(wn); W.w_dst.resize(wn); W.w_len = lens; W.w_cap = caps;
+        W.w_dlen.assign(wn, 0); W.w_st.assign(wn, 0); W.w_sha.resize(20 * wn);
+        chain.resize(wn);
+        for (size_t k = 0; k < wn; k++) {
+            const ExtUnit &u = units[pos + k];
+            const uint64_t off = (uint64_t)u.m * stripe_raw();
+            W.w_src[k] = W.in_arena.as<char>() + ioff[k];
+            W.w_dst[k] = W.out_arena.as<char>() + ooff[k];
+            up.add(static_cast<const char *>(io.src[u.blob]) + off, (void *)W.w_src[k], lens[k]);
+            MfHashDesc &h = chain[k];
+            h.src = static_cast<const uint8_t *>(W.w_src[k]);
+            h.len = lens[k];
+            h.out_index = (uint32_t)k;
+            h.flags = (u.m == 0 ? MF_SHA_FIRST : 0u) | (u.m + 1 == ext_count(io.src_len[u.blob]) ? MF_SHA_LAST : 0u);
+            h.total_len = io.src_len[u.blob];
+            h.state = d_state + 5ull * u.sblob;
+        }
+        rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), true, &up, chain.data());
+        if (rc != MFCAS_OK) break;
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));
+        for (size_t k = 0; k < wn; k++) {
+            const ExtUnit &u = units[pos + k];
+            char *hdst = static_cast<char *>(io.dst[u.blob]) + (uint64_t)u.m * ext_slot();
+            CU(cudaMemcpyAsync(hdst, W.w_dst[k], caps[k], cudaMemcpyDeviceToHost, W.stream));
+            D.d2h += caps[k];
+        }
+        CU(cudaEventRecord(W.ev_done, W.stream));
+        if (phase_timing_on()) CU(cudaEventRecord(W.tl_done, W.stream));
+        W.op = Op::Pack; W.pos = pos; W.wn = wn; W.state = 1;
+        pos = end; w++;
+    }
+    for (size_t k = 0; k < D.ring.size(); k++) {
+        WaveCtx &O = D.ring[(w + k) % D.ring.size()];
+        if (O.state == 1) { int r2 = ext_wave_finish(D, O, io, units); if (rc == MFCAS_OK) rc = r2; }
+    }
+    return rc;
+}
+
 int run_batch(mfcas_ctx *ctx, Op op, uint64_t n, const void *const *src, const uint64_t *src_len,
               void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
     if (!ctx) return MFCAS_E_ARG;
@@ -668,6 +798,37 @@ uint64_t mfcas_pack_bound(uint64_t src_len) { return mf_pack_bound(src_len); }
 int mfcas_pack_batch(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len,
                      void *const *dst, const uint64_t *dst_cap, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
     return run_batch(ctx, Op::Pack, n, src, src_len, dst, dst_cap, dst_len, sha1, status);
+}
+
+uint64_t mfcas_pack_extent_count(uint64_t src_len) { return ext_count(src_len); }
+uint64_t mfcas_pack_extent_bound(uint64_t src_len) { return ext_bound(src_len); }
+
+int mfcas_pack_batch_extents(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len,
+                             void *const *dst, const uint64_t *dst_cap, uint64_t *ext_off, uint64_t *ext_len,
+                             uint8_t *sha1, int32_t *status) {
+    if (!ctx) return MFCAS_E_ARG;
+    if (n == 0) return MFCAS_OK;
+    if (!src || !src_len || !dst || !dst_cap || !ext_off || !ext_len || !sha1 || !status) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t G = ctx->devs.size();
+    std::vector<Shard> shards(G);
+    std::vector<uint64_t> base(n);
+    uint64_t acc = 0;
+    for (uint64_t i = 0; i < n; i++) { shards[i % G].idx.push_back(i); base[i] = acc; acc += ext_count(src_len[i]); }
+    std::vector<int> rcs(G, MFCAS_OK);
+    auto work = [&](size_t g) {
+        ExtIO io{&shards[g], src, src_len, dst, dst_cap, base.data(), ext_off, ext_len, sha1, status};
+        rcs[g] = run_shard_extents(ctx, ctx->devs[g], io);
+    };
+    if (G == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++) th.emplace_back(work, g);
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g] != MFCAS_OK) { ctx->err = ctx->devs[g].err; return rcs[g]; }
+    return MFCAS_OK;
 }
 
 int mfcas_hash_batch(mfcas_ctx *ctx, uint64_t n, const void *const *src, const uint64_t *src_len, uint8_t *sha1, int32_t *status) {

@@ -54,7 +54,8 @@ class LocalStorage(DataStoreStorage):
         fd, tmp = tempfile.mkstemp(dir=os.path.dirname(full_path))
         try:
             with os.fdopen(fd, mode) as f:
-                f.write(data)
+                for piece in getattr(data, "views", (data,)):     # a striped blob is written extent by extent
+                    f.write(piece)
             os.rename(tmp, full_path)
             tmp = None
         finally:

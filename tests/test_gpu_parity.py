@@ -66,7 +66,8 @@ def test_golden_artifacts_and_reference_written_files(gpu_codec, golden):
 def test_edge_sizes_ragged_batch(gpu_codec):
     rng = np.random.default_rng(7)
     sizes = [0, 1, 2, 3, 4, 5, 15, 16, 17, 55, 56, 57, 63, 64, 65, 119, 120, 127, 128, 1023, 1024, 1025, 2047, 2048, 2049,
-             4095, 32767, 32768, 32769, 65535, 65536, 65537, 100000, 0, 1]
+             4095, 32767, 32768, 32769, 65535, 65536, 65537, 100000, 0, 1,
+             2097151, 2097152, 2097153, 4194304 + 77]      # stripe (2 MiB) boundaries of the striped packer
     blobs = []
     for i, n in enumerate(sizes):
         kind = i % 4
@@ -79,6 +80,24 @@ def test_edge_sizes_ragged_batch(gpu_codec):
         else:
             blobs.append(rng.integers(0, 5, n).astype(np.uint8).tobytes())
     _roundtrip(gpu_codec, blobs)
+
+
+def test_striped_and_contiguous_packers_agree(gpu_codec):
+    """mfcas_pack_batch_extents (2 MiB stripes, extents) and mfcas_pack_batch (contiguous, 24 MiB members) give
+    the same keys and decode to the same bytes; a striped blob is a multi-member gzip file."""
+    rng = np.random.default_rng(17)
+    blobs = [rng.standard_normal(n, dtype=np.float32).tobytes() for n in (10, 300000, 1500000, 2500000)] + [b"", bytes(5 << 20)]
+    k1, p1 = gpu_codec.pack_batch(blobs)
+    p1 = [bytes(p) for p in p1]
+    k2, p2 = gpu_codec.pack_batch_contiguous(blobs)
+    p2 = [bytes(p) for p in p2]
+    assert k1 == k2 == [hashlib.sha1(b).hexdigest() for b in blobs]
+    for b, z1, z2 in zip(blobs, p1, p2):
+        assert gzip.decompress(z1) == b and gzip.decompress(z2) == b
+        e, out = c_oracle.gunzip(z1, len(b))
+        assert e == 0 and out == b
+    assert gpu_codec.unpack_batch(p1) == blobs and gpu_codec.unpack_batch(p2) == blobs
+    assert len(p1[3]) > len(p2[3])            # 5 members (one per stripe) instead of 1
 
 
 def test_distributions_and_ratio(gpu_codec):
