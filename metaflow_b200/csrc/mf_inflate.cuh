@@ -38,6 +38,7 @@ struct MfDecMember {
     uint32_t blob, raw_len, crc_expect, first_chunk, n_chunks;
 };
 struct MfDecCounters { uint32_t n_chunks, n_members; };
+#define MF_DEC_MIN_MEMBER_RAW (64ull * MF_CHUNK)      // smallest member size our encoders produce for multi-member blobs (2 MiB stripes)
 
 __device__ __forceinline__ void mf_set_status(int32_t *status, uint32_t blob, int32_t err) { atomicCAS(&status[blob], 0, err); }
 
@@ -80,6 +81,13 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
     if (verdict == 1) { if (lane == 0) { kind[b] = 1; } return; }
     if (verdict >= 16) { if (lane == 0) { kind[b] = 2; status[b] = verdict - 16; dst_len[b] = 0; } return; }
     if (total > blob.dst_cap) { if (lane == 0) { kind[b] = 2; status[b] = MF_DEC_E_DST; dst_len[b] = total; } return; }
+    // per-blob quota, mirrored by the host when it sizes the descriptor arrays (unpack_submit): a blob with more
+    // members / chunks than its destination can account for goes to the lane decoder before any slot is reserved,
+    // so the shared counters can never run past the arrays
+    {
+        const uint64_t qm = blob.dst_cap / MF_DEC_MIN_MEMBER_RAW + 2, qc = blob.dst_cap / MF_CHUNK + qm;
+        if (nmem > qm || nch > qc) { if (lane == 0) kind[b] = 1; return; }
+    }
     uint32_t cbase = 0, mbase = 0;
     if (lane == 0) { cbase = atomicAdd(&counters->n_chunks, nch); mbase = atomicAdd(&counters->n_members, nmem); }
     cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);

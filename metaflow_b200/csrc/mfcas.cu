@@ -401,7 +401,10 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
                   void *const *d_dst, const uint64_t *dst_cap, const CopyPlan *upload) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t max_chunks = 0, max_members = 0;
-    for (uint64_t i = 0; i < n; i++) { max_chunks += dst_cap[i] / MF_CHUNK + 1; max_members += dst_cap[i] / MF_MEMBER_RAW + 2; }
+    for (uint64_t i = 0; i < n; i++) {       // the parse kernel enforces exactly these per-blob quotas
+        const uint64_t qm = dst_cap[i] / MF_DEC_MIN_MEMBER_RAW + 2;
+        max_members += qm; max_chunks += dst_cap[i] / MF_CHUNK + qm;
+    }
     if (max_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
     CU(W.h_desc.ensure(sizeof(MfDecBlob) * n));
     MfDecBlob *hb = W.h_desc.as<MfDecBlob>();
@@ -664,6 +667,7 @@ int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
             const uint64_t len = std::min<uint64_t>(stripe_raw(), io.src_len[u.blob] - off);
             const uint64_t il = align_up(len, 256) + 256, oc = mf_pack_bound(len), ol = align_up(oc, 256) + 256;
             if (end > pos && in_bytes + il + out_bytes + ol > wave_bytes) break;
+            if (end > pos && u.m != units[pos].m) break;      // one piece per blob per launch: the SHA-1 state is carried
             ioff.push_back(in_bytes); ooff.push_back(out_bytes); caps.push_back(oc); lens.push_back(len);
             in_bytes += il; out_bytes += ol; end++;
         }
