@@ -66,7 +66,7 @@ enum class Op { Pack, Hash, Unpack };
 struct WaveCtx {
     cudaStream_t stream = nullptr, stream2 = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_cmp = nullptr, ev_res = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_cmp = nullptr, ev_res = nullptr, ev_done = nullptr, ev_shares = nullptr;
     cudaEvent_t tl_start = nullptr, tl_in = nullptr, tl_res = nullptr, tl_done = nullptr;   // timeline (MFCAS_PHASE_TIMING)
     DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2;
     HostBuf h_desc, h_res;
@@ -86,12 +86,12 @@ struct WaveCtx {
 struct DeviceState {
     int dev = -1;
     cudaStream_t compute = nullptr;      // all chunk-parallel encode kernels of all waves, in submission order
-    cudaStream_t sha_chain = nullptr;    // striped packing: the SHA-1 pieces of all waves, in order (state is carried)
     DevBuf sha_state;                    // 5 words per blob of the running striped call
     std::vector<WaveCtx> ring;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
     float ms[8] = {};
+    cudaEvent_t tl_origin = nullptr;     // MFCAS_PHASE_TIMING: time zero of the current call's wave timeline
 };
 
 }  // namespace
@@ -141,6 +141,7 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
     CU(cudaEventCreateWithFlags(&W.ev_cmp, cudaEventDisableTiming));
     CU(cudaEventCreate(&W.tl_start)); CU(cudaEventCreate(&W.tl_in)); CU(cudaEventCreate(&W.tl_res)); CU(cudaEventCreate(&W.tl_done));
     CU(cudaEventCreateWithFlags(&W.ev_res, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&W.ev_shares, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&W.ev_done, cudaEventDisableTiming));
     return MFCAS_OK;
 }
@@ -148,7 +149,6 @@ int wave_setup(DeviceState &D, WaveCtx &W) {
 int device_setup(DeviceState &D) {
     CU(cudaSetDevice(D.dev));
     CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
-    { int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi)); CU(cudaStreamCreateWithPriority(&D.sha_chain, cudaStreamNonBlocking, hi)); }
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
     CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -169,13 +169,13 @@ void device_teardown(DeviceState &D) {
         W.in_arena.release(); W.out_arena.release(); W.d_desc.release(); W.d_work.release(); W.slots.release();
         W.phase.release(); W.phase2.release(); W.h_desc.release(); W.h_res.release();
         for (auto &e : W.ev) if (e) cudaEventDestroy(e);
-        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_done, W.tl_start, W.tl_in, W.tl_res, W.tl_done}) if (e) cudaEventDestroy(e);
+        if (D.tl_origin) { cudaEventDestroy(D.tl_origin); D.tl_origin = nullptr; }
+        for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_shares, W.ev_done, W.tl_start, W.tl_in, W.tl_res, W.tl_done}) if (e) cudaEventDestroy(e);
         if (W.stream) cudaStreamDestroy(W.stream);
         if (W.stream2) cudaStreamDestroy(W.stream2);
     }
     D.ring.clear();
     if (D.compute) { cudaStreamSynchronize(D.compute); cudaStreamDestroy(D.compute); D.compute = nullptr; }
-    if (D.sha_chain) { cudaStreamSynchronize(D.sha_chain); cudaStreamDestroy(D.sha_chain); D.sha_chain = nullptr; }
     D.sha_state.release();
 }
 
@@ -194,6 +194,36 @@ struct CopyPlan {
         }
         items.push_back({hc, dc, n});
     }
+    // Enqueue the plan.  Runs of equal-sized items at a constant pitch on both sides (the stripes of equally
+    // sized, equally spaced blobs -- a foreach's artifacts) go as ONE pitched copy: a wave of 2 MiB stripes is
+    // then a single DMA descriptor instead of hundreds of back-to-back small copies.
+    cudaError_t run(cudaMemcpyKind kind, cudaStream_t st, uint64_t *bytes) const {
+        size_t i = 0;
+        while (i < items.size()) {
+            const Item &a = items[i];
+            size_t j = i + 1;
+            ptrdiff_t hp = 0, dp = 0;
+            if (j < items.size() && items[j].n == a.n) {
+                hp = items[j].h - a.h; dp = items[j].d - a.d;
+                const ptrdiff_t lim = 0x7FFFFFFF;
+                if (hp >= (ptrdiff_t)a.n && dp >= (ptrdiff_t)a.n && hp <= lim && dp <= lim) {
+                    while (j < items.size() && items[j].n == a.n && items[j].h - items[j - 1].h == hp && items[j].d - items[j - 1].d == dp) j++;
+                } else j = i + 1;
+            }
+            cudaError_t e;
+            if (j - i >= 2) {
+                e = kind == cudaMemcpyHostToDevice ? cudaMemcpy2DAsync(a.d, (size_t)dp, a.h, (size_t)hp, a.n, j - i, kind, st)
+                                                   : cudaMemcpy2DAsync(a.h, (size_t)hp, a.d, (size_t)dp, a.n, j - i, kind, st);
+            } else {
+                j = i + 1;
+                e = kind == cudaMemcpyHostToDevice ? cudaMemcpyAsync(a.d, a.h, a.n, kind, st) : cudaMemcpyAsync(a.h, a.d, a.n, kind, st);
+            }
+            if (e != cudaSuccess) return e;
+            if (bytes) *bytes += (uint64_t)a.n * (j - i);
+            i = j;
+        }
+        return cudaSuccess;
+    }
 };
 
 static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMING") != nullptr; return on; }
@@ -203,11 +233,11 @@ static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMIN
 // small result block (dst_len, status, digests) to pinned host memory; W.ev_res fires when that is there.
 // `upload` (host-pointer API): the wave's input copies; they are enqueued AFTER the small descriptor copy so
 // that nothing small ever queues behind other waves' gigabyte copies on the copy engine.
-// `chain` (striped packing): SHA-1 descriptors of message PIECES (state carried across waves), hashed on
-// D.sha_chain so that the pieces of one blob run in order.
+// `chain` (striped packing): SHA-1 descriptors of message PIECES (state carried across waves); `sha_deps` are
+// the ev_sha events of the in-flight waves that hold the previous piece of any of these blobs.
 int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
                 void *const *d_dst, const uint64_t *dst_cap, bool want_pack, const CopyPlan *upload,
-                const MfHashDesc *chain = nullptr) {
+                const MfHashDesc *chain = nullptr, const std::vector<cudaEvent_t> *sha_deps = nullptr) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
@@ -283,7 +313,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     uint8_t *dw = W.d_work.as<uint8_t>();
     uint8_t *dd = W.d_desc.as<uint8_t>();
     uint8_t *dres = dw + o_res;
-    cudaStream_t s = W.stream, s2 = chain ? D.sha_chain : W.stream2;
+    cudaStream_t s = W.stream, s2 = W.stream2;
     unsigned long long *phase = nullptr;      // MFCAS_PHASE_TIMING=1: per-chunk clock64 at phase boundaries
     if (phase_timing_on() && want_pack && n_chunks) {
         CU(W.phase.ensure(n_chunks * 16 * sizeof(unsigned long long)));
@@ -295,12 +325,13 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     CU(cudaMemsetAsync(dw + o_ticket, 0, sizeof(uint32_t), s));
     if (upload) {
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
-        for (auto &it : upload->items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, s)); D.h2d += it.n; }
+        CU(upload->run(cudaMemcpyHostToDevice, s, &D.h2d));
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
     }
     CU(cudaEventRecord(W.ev_in, s));
     // ---- SHA-1 on the high-priority second stream (serial per blob: it overlaps the chunk-parallel encoder)
     CU(cudaStreamWaitEvent(s2, W.ev_in, 0));
+    if (sha_deps) for (cudaEvent_t e : *sha_deps) CU(cudaStreamWaitEvent(s2, e, 0));   // earlier pieces of these blobs
     CU(cudaEventRecord(W.ev[0], s2));
     // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
     // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
@@ -346,15 +377,19 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         CU(cudaEventRecord(W.ev_cmp, sc));
         CU(cudaStreamWaitEvent(s, W.ev_cmp, 0));
     }
-    CU(cudaStreamWaitEvent(s, W.ev_sha, 0));
-    CU(cudaMemcpyAsync(W.h_res.p, dres, W.res_bytes, cudaMemcpyDeviceToHost, s));
+    // lengths + status follow the encoder on `s` (the caller's bulk copy-back queues right behind them); the
+    // digests follow the SHA-1 kernel on `s2`, so a long hash chain never holds back the copy-back
+    if (want_pack) CU(cudaMemcpyAsync(W.h_res.p, dres, W.r_sha, cudaMemcpyDeviceToHost, s));
     CU(cudaEventRecord(W.ev_res, s));
+    CU(cudaMemcpyAsync(W.h_res.as<uint8_t>() + W.r_sha, dres + W.r_sha, W.res_bytes - W.r_sha, cudaMemcpyDeviceToHost, s2));
+    CU(cudaEventRecord(W.ev_shares, s2));
     W.n = n; W.n_chunks = n_chunks; W.sha_ctas = sha_ctas; W.timed_pack = want_pack;
     return MFCAS_OK;
 }
 
 int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, int32_t *status) {
     CU(cudaEventSynchronize(W.ev_res));
+    CU(cudaEventSynchronize(W.ev_shares));
     const uint8_t *hr = W.h_res.as<uint8_t>();
     const uint64_t n = W.n;
     if (sha1) memcpy(sha1, hr + W.r_sha, 20 * n);
@@ -434,7 +469,7 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + W.res_bytes) - o_kind, s));     // kind, counters, dst_len, status
     if (upload) {
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
-        for (auto &it : upload->items) { CU(cudaMemcpyAsync(it.d, it.h, it.n, cudaMemcpyHostToDevice, s)); D.h2d += it.n; }
+        CU(upload->run(cudaMemcpyHostToDevice, s, &D.h2d));
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
     }
     const MfDecBlob *db = W.d_desc.as<MfDecBlob>();
@@ -511,7 +546,7 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
     if (io.op != Op::Hash) {
         CopyPlan down;
         for (size_t k = 0; k < wn; k++) down.add(io.dst[io.sh->idx[pos + k]], W.w_dst[k], W.w_cap[k]);
-        for (auto &it : down.items) { CU(cudaMemcpyAsync(it.h, it.d, it.n, cudaMemcpyDeviceToHost, W.stream)); D.d2h += it.n; }
+        CU(down.run(cudaMemcpyDeviceToHost, W.stream, &D.d2h));
     }
     CU(cudaEventRecord(W.ev_done, W.stream));
     if (phase_timing_on()) CU(cudaEventRecord(W.tl_done, W.stream));
@@ -520,11 +555,32 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
 }
 
 // everything of the wave is done -> hand the per-blob results to the caller
+// MFCAS_PHASE_TIMING=1: one line per finished wave, milliseconds since the call's first enqueue.
+static void timeline_begin(DeviceState &D, const char *what) {
+    if (!phase_timing_on()) return;
+    if (!D.tl_origin) cudaEventCreate(&D.tl_origin);
+    cudaEventRecord(D.tl_origin, D.ring[0].stream);
+    fprintf(stderr, "[mfcas timeline] %s (ms): units: h2d_start h2d_end | sha_start sha_end | kern_start kern_end | results | out_d2h_end\n", what);
+}
+static void timeline_wave(DeviceState &D, WaveCtx &O, bool unpack, bool pack, size_t units) {
+    if (!phase_timing_on() || !D.tl_origin) return;
+    float a = 0, b = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, e = 0, f = 0;
+    cudaEvent_t t0 = D.tl_origin;
+    cudaEventElapsedTime(&a, t0, O.tl_start); cudaEventElapsedTime(&b, t0, O.tl_in);
+    if (!unpack) { cudaEventElapsedTime(&c0, t0, O.ev[0]); cudaEventElapsedTime(&c1, t0, O.ev[1]); }
+    if (pack) { cudaEventElapsedTime(&d0, t0, O.ev[2]); cudaEventElapsedTime(&d1, t0, O.ev[4]); }
+    if (unpack) { cudaEventElapsedTime(&d0, t0, O.ev[5]); cudaEventElapsedTime(&d1, t0, O.ev[7]); }
+    cudaEventElapsedTime(&e, t0, O.tl_res); cudaEventElapsedTime(&f, t0, O.tl_done);
+    fprintf(stderr, "  %5zu: %6.1f %6.1f | %6.1f %6.1f | %6.1f %6.1f | %6.1f | %6.1f\n", units, a, b, c0, c1, d0, d1, e, f);
+    (void)cudaGetLastError();
+}
+
 int wave_finish(DeviceState &D, WaveCtx &W, const ShardIO &io) {
     int rc = (W.op == Op::Unpack) ? unpack_collect(D, W, W.w_dlen.data(), W.w_st.data())
                                   : pack_collect(D, W, W.w_dlen.data(), W.w_sha.data(), W.w_st.data());
     if (rc != MFCAS_OK) return rc;
     CU(cudaEventSynchronize(W.ev_done));
+    timeline_wave(D, W, W.op == Op::Unpack, W.op == Op::Pack, W.wn);
     if (W.op != Op::Hash) {
         for (size_t k = 0; k < W.wn; k++) {
             uint64_t i = io.sh->idx[W.pos + k];
@@ -548,6 +604,7 @@ int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
     const Shard &sh = *io.sh;
     const uint64_t wave_bytes = ctx->wave_bytes;
     CU(cudaSetDevice(D.dev));
+    timeline_begin(D, io.op == Op::Unpack ? "unpack" : "pack");
     size_t pos = 0, w = 0;
     std::vector<uint64_t> ioff, ooff, caps;
     int rc = MFCAS_OK;
@@ -578,29 +635,13 @@ int run_shard(mfcas_ctx *ctx, DeviceState &D, const ShardIO &io) {
         int r2 = wave_drain(D, O, io);
         if (rc == MFCAS_OK) rc = r2;
     }
-    if (phase_timing_on() && w <= D.ring.size() && rc == MFCAS_OK) {
-        fprintf(stderr, "[mfcas timeline] %s, %zu waves (ms since first H2D): wave: h2d_start h2d_end | sha_start sha_end | enc_start enc_end | results | out_d2h_end\n",
-                io.op == Op::Unpack ? "unpack" : "pack", w);
-        cudaEvent_t t0 = D.ring[0].tl_start;
-        for (size_t k = 0; k < w; k++) {
-            WaveCtx &O = D.ring[k];
-            float a = 0, b = 0, c0 = 0, c1 = 0, d0 = 0, d1 = 0, e = 0, f = 0;
-            cudaEventElapsedTime(&a, t0, O.tl_start); cudaEventElapsedTime(&b, t0, O.tl_in);
-            if (io.op != Op::Unpack) { cudaEventElapsedTime(&c0, t0, O.ev[0]); cudaEventElapsedTime(&c1, t0, O.ev[1]); }
-            if (io.op == Op::Pack) { cudaEventElapsedTime(&d0, t0, O.ev[2]); cudaEventElapsedTime(&d1, t0, O.ev[4]); }
-            if (io.op == Op::Unpack) { cudaEventElapsedTime(&d0, t0, O.ev[5]); cudaEventElapsedTime(&d1, t0, O.ev[7]); }
-            cudaEventElapsedTime(&e, t0, O.tl_res); cudaEventElapsedTime(&f, t0, O.tl_done);
-            fprintf(stderr, "  %2zu: %6.1f %6.1f | %6.1f %6.1f | %6.1f %6.1f | %6.1f | %6.1f\n", k, a, b, c0, c1, d0, d1, e, f);
-        }
-        (void)cudaGetLastError();
-    }
     return rc;
 }
 
 // ------------------------------------------------------------------ striped packing (extent output)
 // A blob is cut into 2 MiB stripes; every stripe becomes its own gzip member in a fixed slot of the blob's
 // destination buffer, and the waves go stripe-major (stripe 0 of every blob, then stripe 1, ...).  The SHA-1
-// of a blob is hashed piecewise (state carried on D.sha_chain), so it progresses while later stripes are still
+// of a blob is hashed piecewise (state carried in HBM, launches ordered by events), so it progresses while later stripes are still
 // on the PCIe bus, and every wave's output goes back as soon as it is encoded.  The packed blob is the
 // concatenation of its extents -- a valid multi-member RFC 1952 file.
 #define MF_STRIPE_CHUNKS 64u
@@ -624,6 +665,7 @@ int ext_wave_finish(DeviceState &D, WaveCtx &W, const ExtIO &io, const std::vect
     int rc = pack_collect(D, W, W.w_dlen.data(), W.w_sha.data(), W.w_st.data());
     if (rc != MFCAS_OK) return rc;
     CU(cudaEventSynchronize(W.ev_done));
+    timeline_wave(D, W, false, true, W.wn);
     for (size_t k = 0; k < W.wn; k++) {
         const ExtUnit &u = units[W.pos + k];
         io.ext_len[io.ext_base[u.blob] + u.m] = W.w_dlen[k];
@@ -652,10 +694,29 @@ int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
     for (uint64_t m = 0; m < maxc; m++)
         for (size_t j = 0; j < sh.idx.size(); j++)
             if (!skip[j] && m < ext_count(io.src_len[sh.idx[j]])) units.push_back({sh.idx[j], (uint32_t)m, (uint32_t)j});
+    timeline_begin(D, "pack, striped");
     CU(D.sha_state.ensure(sh.idx.size() * 5 * sizeof(uint32_t) + 64));
     uint32_t *d_state = D.sha_state.as<uint32_t>();
     const uint64_t wave_bytes = ctx->wave_bytes;
+    auto unit_len = [&](const ExtUnit &u) { return std::min<uint64_t>(stripe_raw(), io.src_len[u.blob] - (uint64_t)u.m * stripe_raw()); };
+    // A wave never holds two pieces of one blob (it stays inside one stripe index), and the waves of a stripe
+    // index are cut evenly, so that no launch is left with a handful of streams: a SHA-1 launch takes as long
+    // as its longest piece whatever its width.
+    std::vector<size_t> per_wave(maxc, 0);
+    {
+        std::vector<uint64_t> g_bytes(maxc, 0), g_count(maxc, 0);
+        for (const ExtUnit &u : units) {
+            const uint64_t len = unit_len(u);
+            g_bytes[u.m] += align_up(len, 256) + 256 + align_up(mf_pack_bound(len), 256) + 256; g_count[u.m]++;
+        }
+        for (uint64_t m = 0; m < maxc; m++) {
+            const uint64_t nw = std::max<uint64_t>(1, (g_bytes[m] + wave_bytes - 1) / wave_bytes);
+            per_wave[m] = (size_t)((g_count[m] + nw - 1) / nw);
+        }
+    }
+    std::vector<long long> last_wave(sh.idx.size(), -1);     // wave that hashed the previous piece of each blob
     std::vector<MfHashDesc> chain;
+    std::vector<cudaEvent_t> deps;
     size_t pos = 0, w = 0;
     int rc = MFCAS_OK;
     while (pos < units.size() && rc == MFCAS_OK) {
@@ -663,11 +724,9 @@ int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
         std::vector<uint64_t> ioff, ooff, caps, lens;
         while (end < units.size()) {
             const ExtUnit &u = units[end];
-            const uint64_t off = (uint64_t)u.m * stripe_raw();
-            const uint64_t len = std::min<uint64_t>(stripe_raw(), io.src_len[u.blob] - off);
+            const uint64_t len = unit_len(u);
             const uint64_t il = align_up(len, 256) + 256, oc = mf_pack_bound(len), ol = align_up(oc, 256) + 256;
-            if (end > pos && in_bytes + il + out_bytes + ol > wave_bytes) break;
-            if (end > pos && u.m != units[pos].m) break;      // one piece per blob per launch: the SHA-1 state is carried
+            if (end > pos && (in_bytes + il + out_bytes + ol > wave_bytes || u.m != units[pos].m || end - pos >= per_wave[u.m])) break;
             ioff.push_back(in_bytes); ooff.push_back(out_bytes); caps.push_back(oc); lens.push_back(len);
             in_bytes += il; out_bytes += ol; end++;
         }
@@ -695,14 +754,27 @@ int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
             h.total_len = io.src_len[u.blob];
             h.state = d_state + 5ull * u.sblob;
         }
-        rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), true, &up, chain.data());
+        deps.clear();
+        {
+            std::vector<long long> seen;
+            for (size_t k = 0; k < wn; k++) {
+                const uint32_t sb = units[pos + k].sblob;
+                const long long lw = last_wave[sb];
+                last_wave[sb] = (long long)w;
+                if (lw < 0 || lw + (long long)D.ring.size() <= (long long)w) continue;      // none, or already collected
+                if (std::find(seen.begin(), seen.end(), lw) == seen.end()) { seen.push_back(lw); deps.push_back(D.ring[lw % D.ring.size()].ev_sha); }
+            }
+        }
+        rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), true, &up, chain.data(), &deps);
         if (rc != MFCAS_OK) break;
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));
-        for (size_t k = 0; k < wn; k++) {
-            const ExtUnit &u = units[pos + k];
-            char *hdst = static_cast<char *>(io.dst[u.blob]) + (uint64_t)u.m * ext_slot();
-            CU(cudaMemcpyAsync(hdst, W.w_dst[k], caps[k], cudaMemcpyDeviceToHost, W.stream));
-            D.d2h += caps[k];
+        {
+            CopyPlan down;
+            for (size_t k = 0; k < wn; k++) {
+                const ExtUnit &u = units[pos + k];
+                down.items.push_back({static_cast<char *>(io.dst[u.blob]) + (uint64_t)u.m * ext_slot(), (char *)W.w_dst[k], (size_t)caps[k]});
+            }
+            CU(down.run(cudaMemcpyDeviceToHost, W.stream, &D.d2h));
         }
         CU(cudaEventRecord(W.ev_done, W.stream));
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_done, W.stream));
