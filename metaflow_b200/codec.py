@@ -12,6 +12,7 @@ import numpy as np
 
 from . import capi
 from .exception import DataException, GpuCasUnavailable
+from .serializer import Segments
 from . import metaflow_config
 
 _ALIGN = 256
@@ -52,6 +53,33 @@ class _PinnedArena(object):
             self._lib.mfcas_free_pinned(self._ptr)
             self._ptr = None
             self.cap = 0
+
+
+class FileSource(object):
+    """A packed blob that still lives in a file: staged with readinto() straight into the pinned arena."""
+
+    __slots__ = ("path", "size")
+
+    def __init__(self, path, size):
+        self.path = path
+        self.size = int(size)
+
+    def __len__(self):
+        return self.size
+
+    def read_into(self, dst, off):
+        view = memoryview(dst)[off:off + self.size]
+        got = 0
+        with open(self.path, "rb", buffering=0) as f:
+            while got < self.size:
+                k = f.readinto(view[got:])
+                if not k:
+                    raise DataException("'%s' is shorter than its size on open (%d of %d bytes)" % (self.path, got, self.size))
+                got += k
+
+    def head(self, n=65536):
+        with open(self.path, "rb", buffering=0) as f:
+            return f.read(min(n, self.size))
 
 
 def _as_u8(blob):
@@ -145,7 +173,13 @@ class GpuCodec(object):
             ln = int(lens[i])
             if ln:
                 o = int(offs[i])
-                arr[o:o + ln] = _as_u8(blobs[i])       # numpy releases the GIL for large copies
+                b = blobs[i]
+                if isinstance(b, Segments):
+                    b.copy_into(arr, o)                # pickle stream pieces + the arrays' own buffers
+                elif isinstance(b, FileSource):
+                    b.read_into(arr, o)                # file -> page-locked memory, no bytes object in between
+                else:
+                    arr[o:o + ln] = _as_u8(b)          # numpy releases the GIL for large copies
 
         if n >= 4 and total >= (64 << 20):
             with ThreadPoolExecutor(max_workers=8) as pool:
@@ -255,25 +289,40 @@ class GpuCodec(object):
             raise UnpackError(rc)
         return size.value, bool(exact.value)
 
+    def _unpacked_size_at(self, ptr, nbytes):
+        size = ctypes.c_uint64(0)
+        exact = ctypes.c_int(0)
+        rc = self._lib.mfcas_unpacked_size(ctypes.c_void_p(ptr), nbytes, ctypes.byref(size), ctypes.byref(exact))
+        if rc != capi.OK:
+            raise UnpackError(rc)
+        return size.value
+
+    accepts_file_sources = True
+
     def unpack_batch(self, packed_blobs, as_bytes=True):
         """-> list with, per blob, the decoded bytes (or a memoryview over pinned memory when
-        as_bytes=False, valid until the next call) or an UnpackError instance."""
+        as_bytes=False, valid until the next call) or an UnpackError instance.
+        Items are bytes-like or `FileSource`s (read straight into the page-locked staging arena)."""
         n = len(packed_blobs)
         if n == 0:
             return []
         results = [None] * n
+        try:
+            all_lens, all_src = self._stage_inputs(packed_blobs)       # staged once, also for retries
+        except OSError as e:
+            raise DataException("could not read a packed blob: %s" % e)
         sizes = np.zeros(n, dtype=np.uint64)
         todo = []
-        for i, p in enumerate(packed_blobs):
+        for i in range(n):
             try:
-                sizes[i], _ = self.unpacked_size(p)
+                sizes[i] = self._unpacked_size_at(int(all_src[i]), int(all_lens[i]))
                 todo.append(i)
             except UnpackError as e:
                 results[i] = e
         attempt = 0
         while todo:
-            blobs = [packed_blobs[i] for i in todo]
-            lens, src = self._stage_inputs(blobs)
+            idx = np.array(todo, dtype=np.int64)
+            lens, src = np.ascontiguousarray(all_lens[idx]), np.ascontiguousarray(all_src[idx])
             m = len(todo)
             caps = np.array([int(sizes[i]) for i in todo], dtype=np.uint64)
             ooffs = np.zeros(m, dtype=np.uint64)

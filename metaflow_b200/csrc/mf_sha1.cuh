@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t s = blockIdx.x * 32u + lane;
-    const bool valid = s < n;
+    const uint32_t spc = one_arg;                          // streams per CTA: 32, or fewer to spread few streams over more SMs
+    const uint32_t s = blockIdx.x * spc + lane;
+    const bool valid = lane < spc && s < n;
     const uint8_t *src = valid ? blobs[s].src : nullptr;
     const uint64_t len = valid ? blobs[s].len : 0;
     const uint64_t nfull = len >> 6;
@@ -200,7 +201,6 @@ __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__rest
             h0 = st[0]; h1 = st[1]; h2 = st[2]; h3 = st[3]; h4 = st[4];
         }
         long long cwait = 0, cstart = dbg ? clock64() : 0;
-        (void)one_arg;
         for (uint64_t i = 0; i < iters; i++) {
             const int bsel = (int)(i & 1);
             { long long t0_ = dbg ? clock64() : 0; mf_bar_sync(MF_BAR_FULL(bsel)); if (dbg) cwait += clock64() - t0_; }

@@ -336,11 +336,13 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
     // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
     // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
-    const unsigned sha_ctas = (unsigned)((n + 31) / 32);
+    static const unsigned sha_spc_env = getenv("MFCAS_SHA_SPC") ? (unsigned)atoi(getenv("MFCAS_SHA_SPC")) : 0u;
+    const unsigned sha_spc = sha_spc_env >= 1 && sha_spc_env <= 32 ? sha_spc_env : 32u;
+    const unsigned sha_ctas = (unsigned)((n + sha_spc - 1) / sha_spc);
     const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
     unsigned long long *sha_dbg = nullptr;
     if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
-    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, 1u);
+    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, sha_spc);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(W.ev[1], s2));

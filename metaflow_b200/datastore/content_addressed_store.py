@@ -112,18 +112,28 @@ class ContentAddressedStore(object):
             yield item
 
     def _load(self, keys, force_raw, is_transfer, as_bytes):
+        for batch in self._load_batches(keys, force_raw, is_transfer, as_bytes):
+            for item in batch:
+                yield item
+
+    def _load_batches(self, keys, force_raw, is_transfer, as_bytes):
+        """Like load_blobs, but yields LISTS of results: one list per decoded GPU window (with as_bytes=False its
+        blobs are views over the codec's page-locked output, valid until the generator is advanced), singletons
+        for everything else.  TaskDataStore.load_artifacts unpickles a window at a time from it."""
         storage = self._storage_impl
         pending = []
         for key in keys:
             blob = self._blob_cache.load_key(key) if self._blob_cache else None
             if blob is not None:
-                yield (key, blob, {"cas_raw": False, "cas_version": 1}) if is_transfer else (key, blob)
+                yield [(key, blob, {"cas_raw": False, "cas_version": 1}) if is_transfer else (key, blob)]
             else:
                 pending.append(self._path_for(key))
         if not pending:
             return
         per_blob_unpack = "_unpack_v1" in self.__dict__ or type(self)._unpack_v1 is not ContentAddressedStore._unpack_v1
         read_files = getattr(storage, "read_files", None)
+        if getattr(self.codec, "accepts_file_sources", False):
+            read_files = self._file_sources          # the codec reads the files itself, into page-locked memory
         with storage.load_bytes(pending) as loaded:
             window, window_bytes = [], 0          # (key, path_key, meta, file_path) of blobs to decode on the GPU
             for path_key, file_path, meta in loaded:
@@ -133,7 +143,7 @@ class ContentAddressedStore(object):
                         blob = f.read()
                     if self._blob_cache:
                         self._blob_cache.store_key(key, blob)
-                    yield (key, blob, meta) if is_transfer else (key, blob)
+                    yield [(key, blob, meta) if is_transfer else (key, blob)]
                     continue
                 if meta is None:
                     unpack_code = self._unpack_backward_compatible  # pre-meta datastores
@@ -156,16 +166,21 @@ class ContentAddressedStore(object):
                             raise DataException("Could not unpack artifact '%s': %s" % (path_key, e))
                     if self._blob_cache:
                         self._blob_cache.store_key(key, blob)
-                    yield (key, blob, meta) if is_transfer else (key, blob)
+                    yield [(key, blob, meta) if is_transfer else (key, blob)]
                     continue
                 window.append((key, path_key, meta, file_path))
                 window_bytes += os.path.getsize(file_path)
                 if window_bytes >= self._window_bytes:
-                    for out in self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes):
-                        yield out
+                    yield list(self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes))
                     window, window_bytes = [], 0
-            for out in self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes):
-                yield out
+            if window:
+                yield list(self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes))
+
+    @staticmethod
+    def _file_sources(paths):
+        from ..codec import FileSource
+
+        return [FileSource(p, os.path.getsize(p)) for p in paths]
 
     @staticmethod
     def _read_window(window, read_files):

@@ -24,6 +24,7 @@ from .. import metaflow_config
 from ..exception import DataException, MetaflowInternalError, UnpicklableArtifactException
 from ..metadata_provider import DataArtifact, MetaDatum
 from ..parameters import Parameter
+from ..serializer import dumps_segments, loads_batch
 from ..util import Path, is_stringish, to_fileobj
 
 _included_file_type = "<class 'metaflow.includefile.IncludedFile'>"
@@ -60,6 +61,18 @@ def require_mode(mode):
 class ArtifactTooLarge(object):
     def __str__(self):
         return "< artifact too large >"
+
+
+_pool = None
+
+
+def _unpickle_pool():
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix="mf-unpickle")
+    return _pool
 
 
 class TaskDataStore(object):
@@ -212,7 +225,7 @@ class TaskDataStore(object):
         def blobs():
             for name, obj in artifacts_iter:
                 try:
-                    blob = pickle.dumps(obj, protocol=4)
+                    blob = dumps_segments(obj)         # the bytes of pickle.dumps(obj, protocol=4), arrays by reference
                 except TypeError as e:
                     raise UnpicklableArtifactException(name) from e
                 self._info[name] = {"size": len(blob), "type": str(type(obj)), "encoding": "gzip+pickle-v4"}
@@ -236,14 +249,23 @@ class TaskDataStore(object):
             if encoding not in self._encodings:
                 raise DataException("Python 3.6 or later is required to load artifact '%s'" % name)
             by_key[self._objects[name]].append(name)
-        loader = getattr(self._ca_store, "_load", None)
-        if loader is not None:
-            stream = loader(by_key.keys(), False, False, as_bytes=False)  # views over the pinned arena
-        else:
-            stream = self._ca_store.load_blobs(by_key.keys())
-        for key, blob in stream:
-            for name in by_key[key]:
-                yield name, pickle.loads(blob)
+        loader = getattr(self._ca_store, "_load_batches", None)
+        if loader is None:
+            for key, blob in self._ca_store.load_blobs(by_key.keys()):
+                for name in by_key[key]:
+                    yield name, pickle.loads(blob)
+            return
+        # one decoded GPU window at a time: the blobs are views over the codec's page-locked output, and
+        # the whole window is unpickled before the generator moves on (payload copies on a thread pool)
+        for batch in loader(by_key.keys(), False, False, as_bytes=False):
+            names, blobs = [], []
+            for key, blob in batch:
+                for name in by_key[key]:          # every name gets its own object (task_datastore.py:439-442)
+                    names.append(name)
+                    blobs.append(blob)
+            big = sum(len(b) for b in blobs) >= (8 << 20) and len(blobs) > 1
+            for name, obj in zip(names, loads_batch(blobs, _unpickle_pool() if big else None)):
+                yield name, obj
 
     @require_mode("r")
     def get_artifact_sizes(self, names):

@@ -1,7 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "=== full default bench (with cpu baseline)"; S=$(date +%s); timeout 1700 python bench.py 2> gpurun_out/bench_default.err; echo "elapsed $(( $(date +%s) - S )) s"; tail -3 gpurun_out/bench_default.err
-echo "=== reference arm"; S=$(date +%s); timeout 900 python bench.py --impl reference --steps 2 --warmup 1 2> gpurun_out/bench_ref.err; echo "elapsed $(( $(date +%s) - S )) s"; tail -3 gpurun_out/bench_ref.err
+echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30
+echo "=== api profile 64"; timeout 600 python tools/api_profile.py 64 2>&1 | tail -12
+echo "=== api profile 256"; timeout 600 python tools/api_profile.py 256 2>&1 | tail -12
 } > gpurun_out/run11.log 2>&1
-tail -c 6000 gpurun_out/run11.log
+tail -c 4000 gpurun_out/run11.log

@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:mf_ -c 100 --csv --log-file gpurun_out/r01_final_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --api-blobs 0 > gpurun_out/ncu_list.log 2>&1; tail -1 gpurun_out/ncu_list.log | cut -c1-200
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"mf_inflate_chunk_kernel" -s 1 -c 1 -o gpurun_out/r01_final_inflate -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline --api-blobs 0 > gpurun_out/ncu_full2.log 2>&1; tail -2 gpurun_out/ncu_full2.log | cut -c1-200
+echo "=== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -30
+for spc in 32 16 8; do
+echo "=== bench SHA_SPC=$spc"; MFCAS_SHA_SPC=$spc timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --api-blobs 0 --wave-mib 1024 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['kernel_ms_per_step'], d['e2e']['save_GBps'], d['e2e']['load_GBps'])"
+done
+echo "=== api profile 64"; timeout 600 python tools/api_profile.py 64 2>&1 | tail -9
+echo "=== api profile 256"; timeout 600 python tools/api_profile.py 256 2>&1 | tail -9
+echo "=== api profile 256 SPC=8 timeline"; MFCAS_SHA_SPC=8 MFCAS_PHASE_TIMING=1 timeout 600 python tools/api_profile.py 256 2>&1 | grep -v "phase\]" | tail -120
 } > gpurun_out/run12.log 2>&1
-tail -c 1500 gpurun_out/run12.log
+tail -c 3000 gpurun_out/run12.log
