@@ -96,11 +96,11 @@ __device__ __forceinline__ void mf_mbar_wait(void *bar, uint32_t parity) {
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order
 __global__ void __launch_bounds__(96, 1) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
-                                                      unsigned long long *__restrict__ dbg, uint32_t one_arg) {
+                                                      unsigned long long *__restrict__ dbg, uint32_t spc, uint32_t *__restrict__ gate) {
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     MfShaSmem &S = *reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t spc = one_arg;                          // streams per CTA: 32, or fewer to spread few streams over more SMs
+    if (gate && threadIdx.x == 0) atomicAdd(gate, 1u);      // "this CTA is resident": the host holds the encoder back until all are
     const uint32_t s = blockIdx.x * spc + lane;
     const bool valid = lane < spc && s < n;
     const uint8_t *src = valid ? blobs[s].src : nullptr;

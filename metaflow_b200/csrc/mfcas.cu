@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <cuda.h>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -74,7 +75,7 @@ struct WaveCtx {
     int state = 0;                       // 0 idle, 1 kernels in flight, 2 output D2H in flight
     Op op = Op::Pack;
     uint64_t n = 0, n_chunks = 0;
-    unsigned sha_ctas = 0;
+    unsigned sha_ctas = 0; bool sha_excl = false;
     size_t r_len = 0, r_st = 0, r_sha = 0, res_bytes = 0;
     bool timed_pack = false;
     size_t pos = 0, wn = 0;              // slice [pos, pos+wn) of the shard (host-pointer API)
@@ -87,6 +88,7 @@ struct DeviceState {
     int dev = -1;
     cudaStream_t compute = nullptr;      // all chunk-parallel encode kernels of all waves, in submission order
     DevBuf sha_state;                    // 5 words per blob of the running striped call
+    DevBuf gate;                         // one word: SHA-1 CTAs resident (device-resident packing, see pack_submit)
     std::vector<WaveCtx> ring;
     std::string err;
     uint64_t launches = 0, h2d = 0, d2h = 0;
@@ -127,8 +129,13 @@ struct Carver {
 };
 
 #define MF_RING 8
-// encoder CTAs resident at once: 2 per SM x 148 SMs minus 24, i.e. ~24 SMs keep one free 100+ KB slot for SHA-1 CTAs
+// Encoder CTAs resident at once.  An SM holds two 100+ KB CTAs -- encoder or SHA-1 (which asks for 112 KB so that
+// nothing else shares its schedulers).  The persistent encoder grid is sized to leave one such slot per SHA-1 CTA
+// that may be running beside it; otherwise whichever kernel's CTAs are dispatched first owns the SMs and the hash
+// chain (the longest pole of a wave) waits for the whole encoder.
+#define MF_SM_SLOTS (2u * 148u)
 #define MF_ENC_GRID_CAP 272u
+#define MF_ENC_GRID_MIN 168u
 
 int wave_setup(DeviceState &D, WaveCtx &W) {
     int lo = 0, hi = 0;
@@ -154,6 +161,11 @@ int device_setup(DeviceState &D) {
     CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
+    // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
+    // split differs, and re-splitting needs the SM idle -- with the driver's per-kernel default the hash CTAs wait
+    // for the persistent encoder to drain whenever the encoder happens to be dispatched first.  Same split for both.
+    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     mf_init_tables_kernel<<<2, 256, 0, D.ring[0].stream>>>();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(D.ring[0].stream));
@@ -177,6 +189,7 @@ void device_teardown(DeviceState &D) {
     D.ring.clear();
     if (D.compute) { cudaStreamSynchronize(D.compute); cudaStreamDestroy(D.compute); D.compute = nullptr; }
     D.sha_state.release();
+    D.gate.release();
 }
 
 // Copies a set of (host ptr, device ptr, len) with runs of contiguous pairs merged into one memcpy.
@@ -225,6 +238,15 @@ struct CopyPlan {
         return cudaSuccess;
     }
 };
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+// the driver entry point, fetched through the runtime so that the library does not link libcuda
+static StreamWaitValue32Fn stream_wait_value_fn() {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return reinterpret_cast<StreamWaitValue32Fn>(fn);
+}
 
 static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMING") != nullptr; return on; }
 
@@ -328,6 +350,20 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         CU(upload->run(cudaMemcpyHostToDevice, s, &D.h2d));
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
     }
+    // Device-resident packing is ONE wave: a hash kernel that runs as long as its longest blob beside one long
+    // persistent encoder.  Which of the two is dispatched first decides whether the hash CTAs get SMs of their own
+    // (two 112 KB CTAs fill an SM) or share schedulers with encoder warps (13 % slower chain).  Make it
+    // deterministic: the encoder's stream waits (cuStreamWaitValue32) until every hash CTA has reported in.
+    static const StreamWaitValue32Fn wait_value = stream_wait_value_fn();
+    uint32_t *gate = nullptr;
+    const unsigned sha_spc = 32u;             // streams per CTA (measured: half-filled warps are no faster per stream)
+    const unsigned sha_ctas = (unsigned)((n + sha_spc - 1) / sha_spc);
+    const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
+    if (!upload && !chain && want_pack && sha_smem > sizeof(MfShaSmem) && sha_ctas <= 64 && wait_value) {
+        CU(D.gate.ensure(256));
+        gate = D.gate.as<uint32_t>();
+        CU(cudaMemsetAsync(gate, 0, sizeof(uint32_t), s));          // before ev_in: both kernels' streams wait on it
+    }
     CU(cudaEventRecord(W.ev_in, s));
     // ---- SHA-1 on the high-priority second stream (serial per blob: it overlaps the chunk-parallel encoder)
     CU(cudaStreamWaitEvent(s2, W.ev_in, 0));
@@ -336,13 +372,10 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
     // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
     // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
-    static const unsigned sha_spc_env = getenv("MFCAS_SHA_SPC") ? (unsigned)atoi(getenv("MFCAS_SHA_SPC")) : 0u;
-    const unsigned sha_spc = sha_spc_env >= 1 && sha_spc_env <= 32 ? sha_spc_env : 32u;
-    const unsigned sha_ctas = (unsigned)((n + sha_spc - 1) / sha_spc);
-    const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
     unsigned long long *sha_dbg = nullptr;
     if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
-    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, sha_spc);
+    W.sha_ctas = sha_ctas; W.sha_excl = sha_smem > sizeof(MfShaSmem);
+    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, sha_spc, gate);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(W.ev[1], s2));
@@ -350,9 +383,15 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     if (want_pack) {
         cudaStream_t sc = D.compute;          // one encoder kernel at a time per device (see MF_ENC_GRID_CAP)
         CU(cudaStreamWaitEvent(sc, W.ev_in, 0));
+        if (gate && wait_value((CUstream)sc, (CUdeviceptr)(uintptr_t)gate, sha_ctas, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
+            D.err = "cuStreamWaitValue32 failed"; return MFCAS_E_CUDA;
+        }
         CU(cudaEventRecord(W.ev[2], sc));
         if (n_chunks) {
-            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, MF_ENC_GRID_CAP), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
+            unsigned sha_slots = 0;           // exclusive SHA-1 CTAs of this wave and of the waves still in flight
+            for (WaveCtx &O : D.ring) if ((&O == &W || O.state == 1) && O.sha_excl) sha_slots += O.sha_ctas;
+            const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, std::min(MF_ENC_GRID_CAP, MF_SM_SLOTS - std::min(sha_slots, MF_SM_SLOTS)));
+            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
                 reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket));

@@ -28,7 +28,7 @@ class ContentAddressedStore(object):
         self._blob_cache = None
         self._codec = codec
         # bytes of raw blobs gathered before a GPU batch is issued
-        self._window_bytes = int(metaflow_config.GPU_CAS_WAVE_BYTES)
+        self._window_bytes = int(metaflow_config.GPU_CAS_WINDOW_BYTES)
 
     # -- plumbing ----------------------------------------------------------------------
     @property

@@ -12,6 +12,7 @@ GPUs); load_artifacts (:386-442) loads all requested keys as one batch and unpic
 of the page-locked output arena.
 """
 import json
+import os
 import pickle
 import sys
 import time
@@ -71,7 +72,7 @@ def _unpickle_pool():
     if _pool is None:
         from concurrent.futures import ThreadPoolExecutor
 
-        _pool = ThreadPoolExecutor(max_workers=8, thread_name_prefix="mf-unpickle")
+        _pool = ThreadPoolExecutor(max_workers=max(2, min(16, len(os.sched_getaffinity(0)))), thread_name_prefix="mf-unpickle")
     return _pool
 
 

@@ -31,5 +31,9 @@ PROFILE_FROM_START = from_conf("PROFILE_FROM_START", False)
 
 # New knobs for the GPU path (SURVEY.md section 5 proposal).
 GPU_CAS_DEVICES = from_conf("GPU_CAS_DEVICES", "")            # "" = all visible; else "0,1,.."
-GPU_CAS_WAVE_BYTES = from_conf("GPU_CAS_WAVE_BYTES", 1 << 30)  # bytes of blobs packed per GPU wave
+GPU_CAS_WAVE_BYTES = from_conf("GPU_CAS_WAVE_BYTES", 1 << 30)  # bytes (in + out) staged per pipelined GPU wave
+# bytes of blobs gathered from a save/load iterator before one codec call is issued.  SHA-1 is a serial chain per
+# blob (~8 ms per MiB on a GPU lane), so a call is only as fast as it is WIDE: the window should hold as many
+# blobs as the caller has (the page-locked staging arenas grow on demand up to in + out of this size).
+GPU_CAS_WINDOW_BYTES = from_conf("GPU_CAS_WINDOW_BYTES", 4 << 30)
 GPU_CAS_LZ = from_conf("GPU_CAS_LZ", 1)                        # 0 = Huffman-only encoder
