@@ -299,63 +299,81 @@ def run_ours(args, rank, world, local_rank):
     ecount = lib.mfcas_pack_extent_count(blob_len)
     ecap = lib.mfcas_pack_extent_bound(blob_len)
     estride = (ecap + 255) // 256 * 256 + 256
-    h_in_p = lib.mfcas_alloc_pinned(B * stride); h_pk_p = lib.mfcas_alloc_pinned(B * estride); h_out_p = lib.mfcas_alloc_pinned(B * stride)
+    # the step's blobs go through the host API in sub-batches of <= 1024 (17 GB): the path is PCIe-bound, so its
+    # rate does not depend on the batch, and the page-locked buffers stay at 3 x 17 GB per rank
+    ne = min(n, 1024)
+    assert n % ne == 0, "--blobs-per-step must be a multiple of 1024 (or smaller than it)"
+    h_in_p = lib.mfcas_alloc_pinned(ne * stride); h_pk_p = lib.mfcas_alloc_pinned(ne * estride); h_out_p = lib.mfcas_alloc_pinned(ne * stride)
     assert h_in_p and h_pk_p and h_out_p, "pinned allocation failed"
-    h_in = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_in_p))
-    h_out = np.ctypeslib.as_array((ctypes.c_uint8 * (B * stride)).from_address(h_out_p))
-    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (B * estride)).from_address(h_pk_p))
-    hsrc = (vp * n)(*[h_in_p + i * stride for i in range(n)])
-    hpk = (vp * n)(*[h_pk_p + i * estride for i in range(n)])
-    hout = (vp * n)(*[h_out_p + i * stride for i in range(n)])
-    epcap = (u64 * n)(*([ecap] * n))
-    ext_off = (u64 * (n * ecount))()
-    ext_len = (u64 * (n * ecount))()
+    h_in = np.ctypeslib.as_array((ctypes.c_uint8 * (ne * stride)).from_address(h_in_p))
+    h_out = np.ctypeslib.as_array((ctypes.c_uint8 * (ne * stride)).from_address(h_out_p))
+    h_pk = np.ctypeslib.as_array((ctypes.c_uint8 * (ne * estride)).from_address(h_pk_p))
+    hsrc = (vp * ne)(*[h_in_p + i * stride for i in range(ne)])
+    hpk = (vp * ne)(*[h_pk_p + i * estride for i in range(ne)])
+    hout = (vp * ne)(*[h_out_p + i * stride for i in range(ne)])
+    epcap = (u64 * ne)(*([ecap] * ne))
+    eslen = (u64 * ne)(*([blob_len] * ne))
+    eplen = (u64 * ne)()
+    eocap = (u64 * ne)(*([blob_len] * ne))
+    eolen = (u64 * ne)()
+    est = (ctypes.c_int32 * ne)()
+    esha = ctypes.create_string_buffer(20 * ne)
+    ext_off = (u64 * (ne * ecount))()
+    ext_len = (u64 * (ne * ecount))()
     t_in = torch.from_numpy(h_in)
     e2e_save = e2e_load = 0.0
     e2e_steps = args.steps
     h2d = d2h = 0
 
+    def echeck(rc, what):
+        if rc != 0 or any(est):
+            raise SystemExit("%s failed rc=%d status=%s: %s" % (what, rc, [x for x in est if x][:4], lib.mfcas_last_error(ctx)))
+
     def save_host():
         t0 = time.perf_counter()
-        check(lib.mfcas_pack_batch_extents(ctx, n, hsrc, slen, hpk, epcap, ext_off, ext_len, sha, st), "pack_batch_extents")
+        echeck(lib.mfcas_pack_batch_extents(ctx, ne, hsrc, eslen, hpk, epcap, ext_off, ext_len, esha, est), "pack_batch_extents")
         return time.perf_counter() - t0
 
     def compact_host():
         """extents -> contiguous packed blob at the start of its slot (what writev into the CAS file does)"""
-        eo = np.frombuffer(ext_off, dtype=np.uint64).reshape(n, ecount)
-        el = np.frombuffer(ext_len, dtype=np.uint64).reshape(n, ecount)
-        for i in range(n):
+        eo = np.frombuffer(ext_off, dtype=np.uint64).reshape(ne, ecount)
+        el = np.frombuffer(ext_len, dtype=np.uint64).reshape(ne, ecount)
+        for i in range(ne):
             base, cur = i * estride, int(el[i, 0])
             for k in range(1, ecount):
                 o, ln = int(eo[i, k]), int(el[i, k])
                 h_pk[base + cur:base + cur + ln] = h_pk[base + o:base + o + ln]
                 cur += ln
-            plen[i] = cur
+            eplen[i] = cur
 
     def load_host():
         t0 = time.perf_counter()
-        check(lib.mfcas_unpack_batch(ctx, n, hpk, plen, hout, ocap, olen, st), "unpack_batch")
+        echeck(lib.mfcas_unpack_batch(ctx, ne, hpk, eplen, hout, eocap, eolen, est), "unpack_batch")
         return time.perf_counter() - t0
 
-    generate(20_000); t_in.copy_(d_in); torch.cuda.synchronize(); save_host(); compact_host(); load_host()       # warm-up (arena allocation)
+    def refresh(part):
+        t_in.copy_(d_in[part * ne * stride:(part + 1) * ne * stride])     # device -> page-locked host buffer (untimed)
+
+    generate(20_000); refresh(0); torch.cuda.synchronize(); save_host(); compact_host(); load_host()       # warm-up (arena allocation)
     import gzip
     import hashlib
     blob0 = h_in[:blob_len].tobytes()
-    assert sha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
-    assert gzip.decompress(h_pk[:plen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"
+    assert esha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
+    assert gzip.decompress(h_pk[:eplen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"
     barrier()
     for s in range(e2e_steps):
         generate(30_000 + s)
-        t_in.copy_(d_in)                     # device -> page-locked host buffer (untimed: it only refreshes the inputs)
-        barrier()
-        a = save_host()
-        compact_host()
-        barrier()
-        b = load_host()
-        e2e_save += a; e2e_load += b
-        pb = sum(plen)
-        h2d += n * blob_len + pb; d2h += n * ecap + n * blob_len
-    assert h_out[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes() == h_in[(n - 1) * stride:(n - 1) * stride + blob_len].tobytes()
+        for part in range(n // ne):
+            refresh(part)
+            barrier()
+            a = save_host()
+            compact_host()
+            barrier()
+            b = load_host()
+            e2e_save += a; e2e_load += b
+            pb = sum(eplen)
+            h2d += ne * blob_len + pb; d2h += ne * ecap + ne * blob_len
+    assert h_out[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes() == h_in[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes()
 
     # ---- L-api (SURVEY 8d): objects -> TaskDataStore.save_artifacts -> files on tmpfs -> load_artifacts -> objects,
     # pickle and filesystem included; a bounded sample of the same arrays (rank 0 only, informational)
@@ -418,7 +436,9 @@ def run_ours(args, rank, world, local_rank):
         tpath = os.path.join(REPO, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(names[dominant])
+                tj = json.load(f)
+            per_blob = tj.get("per_blob", {}).get(names[dominant])     # measured with ncu on tj["blobs"] blobs of this size; linear in blobs
+            traffic = per_blob * n if per_blob else None
         cpu = None
         if not args.no_cpu_baseline:
             cores = usable_cores()
@@ -434,7 +454,8 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts (pickle blob %d B), save+load" % blob_len,
                        "blobs_per_step_per_gpu": n, "blobs_total": n * args.steps * world, "sharding": "round-robin blob i -> rank i mod N, no collective",
-                       "l2": "inputs %.1f GB per step >> 126 MB L2 (no flush needed)" % (n * blob_len / 1e9), "packed_ratio": ratio},
+                       "l2": "inputs %.1f GB per step >> 126 MB L2 (no flush needed)" % (n * blob_len / 1e9), "packed_ratio": ratio,
+                       "e2e_sub_batch": ne, "wave_mib": args.wave_mib},
             "save_GBps": total_raw / (t_save * 1e-3) / 1e9, "load_GBps": total_raw / (t_load * 1e-3) / 1e9,
             "kernel_ms_per_step": {nm: k / args.steps for nm, k in zip(names, kms)},
             "roofline": {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -460,8 +481,8 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blobs-per-step", type=int, default=1024)
-    ap.add_argument("--wave-mib", type=int, default=4096, help="bytes (in+out) per pipelined wave of the host-pointer API")
+    ap.add_argument("--blobs-per-step", type=int, default=2048)
+    ap.add_argument("--wave-mib", type=int, default=1024, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--api-blobs", type=int, default=64, help="artifacts in the L-api (objects <-> tmpfs files) sample; 0 = skip")

@@ -80,12 +80,18 @@ __global__ void mf_init_tables_kernel() {
 
 // raw (zero-init, no final xor) CRC of `n` bytes (n multiple of 4) at smem offset `off` (multiple of 4)
 __device__ __forceinline__ uint32_t mf_crc_words(const uint8_t *s, uint32_t off, uint32_t n, const uint32_t (*T)[256]) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(s + off);
     uint32_t crc = 0;
-    for (uint32_t i = 0; i < (n >> 2); i++) {
-        uint32_t x = crc ^ w[i];
-        crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24];
+#define MF_CRC_STEP(word) { const uint32_t x = crc ^ (word); crc = T[3][x & 0xFFu] ^ T[2][(x >> 8) & 0xFFu] ^ T[1][(x >> 16) & 0xFFu] ^ T[0][x >> 24]; }
+    if (n == 64u && (off & 15u) == 0) {
+        // a whole 64-byte piece: four 16-byte loads (word loads at the 64-byte lane stride are 16-way bank conflicts)
+        const uint4 *v = reinterpret_cast<const uint4 *>(s + off);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const uint4 u = v[q]; MF_CRC_STEP(u.x) MF_CRC_STEP(u.y) MF_CRC_STEP(u.z) MF_CRC_STEP(u.w) }
+        return crc;
     }
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(s + off);
+    for (uint32_t i = 0; i < (n >> 2); i++) MF_CRC_STEP(w[i])
+#undef MF_CRC_STEP
     return crc;
 }
 
@@ -375,9 +381,80 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
     return base;      // header length in bits
 }
 
+// Device form of mf_lane_emit (mf_core.h keeps the portable one for the CPU model): same tokens, same bits.
+// The portable loop reads the segment a byte at a time at a 32-byte lane stride -- an 8-way bank conflict per
+// read, twice per chunk, which made the two sweeps the shared-memory bottleneck of the encoder.  Here a lane
+// takes its 32-byte span with two 16-byte loads and walks it out of registers (fully unrolled, static byte
+// extraction); the counting sweep looks lengths up in the byte table (72 words: mostly broadcast).
+template <bool WRITE>
+__device__ __forceinline__ uint32_t mf_lane_emit_dev(const uint8_t *seg, uint32_t seglen, const uint32_t *matches, uint32_t nmatch,
+                                                     uint32_t lane, const uint32_t *ll_codes, const uint8_t *ll_lens,
+                                                     const uint32_t *d_codes, MfBitWriter *w) {
+    const uint32_t lo = lane * 32u;
+    const uint32_t hi = min(lo + 32u, seglen);
+    if (lo >= hi) return 0;
+    uint32_t wd[8];
+    {
+        const uint4 v0 = *reinterpret_cast<const uint4 *>(seg + lo), v1 = *reinterpret_cast<const uint4 *>(seg + lo + 16);
+        wd[0] = v0.x; wd[1] = v0.y; wd[2] = v0.z; wd[3] = v0.w; wd[4] = v1.x; wd[5] = v1.y; wd[6] = v1.z; wd[7] = v1.w;
+    }
+    uint32_t a = 0, b = nmatch;
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (mf_match_pos(matches[mid]) < lo) a = mid + 1; else b = mid; }
+    uint32_t mi = a;
+    uint32_t p = lo;
+    if (mi > 0) { const uint32_t pm = matches[mi - 1]; const uint32_t e = mf_match_pos(pm) + mf_match_len(pm); if (e > p) p = e; }
+    uint32_t next_pos = mi < nmatch ? mf_match_pos(matches[mi]) : 0xFFFFFFFFu;
+    uint32_t bits = 0;
+    // literal-only span (no match starts in it, none reaches into it): no token bookkeeping at all.  Two literals
+    // are joined (<= 30 bits) before they go to the bit writer, so the 64-bit accumulate runs 16 times, not 32.
+    if (p == lo && next_pos >= hi && hi == lo + 32u) {
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+            const uint32_t b0 = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu, b1 = (wd[k >> 2] >> (((k + 1) & 3) * 8)) & 0xFFu;
+            if (WRITE) {
+                const uint32_t e0 = ll_codes[b0], e1 = ll_codes[b1];
+                const uint32_t l0 = e0 >> 16, l1 = e1 >> 16;
+                w->put((e0 & 0xFFFFu) | ((e1 & 0xFFFFu) << l0), l0 + l1);
+                bits += l0 + l1;
+            } else {
+                bits += (uint32_t)ll_lens[b0] + (uint32_t)ll_lens[b1];
+            }
+        }
+        return bits;
+    }
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t pos = lo + (uint32_t)k;
+        if (pos < hi && pos == p) {
+            if (pos == next_pos) {
+                const uint32_t m = matches[mi];
+                const uint32_t len = mf_match_len(m), dist = mf_match_dist(m);
+                uint32_t ls, lb, lv, ds, db, dv;
+                mf_len_sym(len, ls, lb, lv); mf_dist_sym(dist, ds, db, dv);
+                const uint32_t le = ll_codes[ls], de = d_codes[ds];
+                bits += (le >> 16) + lb + (de >> 16) + db;
+                if (WRITE) {
+                    w->put((le & 0xFFFFu) | (lv << (le >> 16)), (le >> 16) + lb);
+                    w->put((de & 0xFFFFu) | (dv << (de >> 16)), (de >> 16) + db);
+                }
+                p += len; mi++;
+                next_pos = mi < nmatch ? mf_match_pos(matches[mi]) : 0xFFFFFFFFu;
+            } else {
+                const uint32_t byte = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                if (WRITE) { const uint32_t e = ll_codes[byte]; bits += e >> 16; w->put(e & 0xFFFFu, e >> 16); }
+                else bits += ll_lens[byte];
+                p++;
+            }
+        }
+    }
+    return bits;
+}
+
 #define MF_ENC_THREADS 512
 #define MF_ENC_WARPS 16
 #define MF_HASH_BITS 10
+#define MF_ENC_GROUP 16u         // consecutive chunks of a member handed to one CTA: codes may be carried inside a group
+#define MF_HDR_CACHE_WORDS 192u
 #define MF_REGION_B 34816u      // hash tables in pass 2 (32 KiB), packed output words afterwards
 
 struct __align__(16) MfEncSmem {
@@ -403,6 +480,11 @@ struct __align__(16) MfEncSmem {
     uint32_t total_bits;
     uint32_t comp_bytes;
     uint32_t stored;
+    // the codes of the previous chunk of this group, kept while they stay within 1/128 of what a rebuild could give
+    uint32_t hdr_cache[MF_HDR_CACHE_WORDS];   // its block header, bit for bit (every chunk starts byte-aligned)
+    uint32_t cache_hdr_bits;                  // 0: nothing cached
+    float cache_red16;                        // redundancy of the cached code on the chunk it was built for, bits*16 per symbol
+    uint32_t dec_cost, dec_miss, dec_a_ll, dec_b_ll, dec_a_d, dec_b_d;   // this chunk against the cached code lengths
 };
 
 // flags bit 0: MFCAS_FLAG_NO_LZ
@@ -410,7 +492,8 @@ __global__ void __launch_bounds__(MF_ENC_THREADS, 2)
 mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__restrict__ chunk_member, uint32_t n_chunks_total,
                   uint8_t *__restrict__ slots, uint32_t *__restrict__ comp_bytes_out, uint16_t *__restrict__ hdr_bits_out,
                   uint16_t *__restrict__ seg_bits_out, uint32_t *__restrict__ chunk_crc_out, uint32_t flags,
-                  unsigned long long *__restrict__ phase_clk, uint32_t *__restrict__ ticket) {
+                  unsigned long long *__restrict__ phase_clk, uint32_t *__restrict__ ticket,
+                  const uint32_t *__restrict__ grp_first, uint32_t n_groups) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfEncSmem &S = *reinterpret_cast<MfEncSmem *>(mf_smem_raw);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -418,15 +501,25 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     // a free slot for the latency-critical SHA-1 CTAs of this and the following waves
     // Chunks are handed out by an atomic ticket, not by a static stride: CTAs that share their SM with SHA-1
     // CTAs run slower, and a static partition would make everyone wait for them.
+    // The unit of work is a GROUP of up to MF_ENC_GROUP consecutive chunks of one member.  Building the two Huffman
+    // codes and the block header is warp-serial work (half of a chunk's cycles); inside a group the codes of the
+    // previous chunk are kept whenever they cost no more than 1/128 above what fresh codes could (pass 3a), which on
+    // stationary data (float arrays) is nearly always.  Groups are member-relative, so a member's bytes do not
+    // depend on the batch it was packed in or on which CTA took which ticket.
+    (void)n_chunks_total;
     for (;;) {
         if (tid == 0) S.ticket = atomicAdd(ticket, 1u);
         __syncthreads();
-        const uint32_t c = S.ticket;
-        if (c >= n_chunks_total) break;
+        const uint32_t grp = S.ticket;
+        if (grp >= n_groups) break;
+        const uint32_t c0 = grp_first[grp];
+        const MfEncMember mem = members[chunk_member[c0]];
+        const uint32_t c1 = min(c0 + MF_ENC_GROUP, mem.first_chunk + mem.n_chunks);
+        if (tid == 0) S.cache_hdr_bits = 0;
+    for (uint32_t c = c0; c < c1; c++) {
     // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
 #define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 16 + (k)] = clock64(); } while (0)
     MF_PHASE(0);
-    const MfEncMember mem = members[chunk_member[c]];
     const uint32_t ci = c - mem.first_chunk;
     const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
     const uint8_t *src = mem.src + (size_t)ci * MF_CHUNK;
@@ -441,6 +534,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
         for (uint32_t i = tid; i < 1024; i += MF_ENC_THREADS) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
         for (uint32_t i = tid; i < 288; i += MF_ENC_THREADS) S.ll_hist[i] = 0;
         if (tid < 32) S.d_hist[tid] = 0;
+        if (tid == 0) { S.dec_cost = 0; S.dec_miss = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }
     }
     __syncthreads();
     // bytes past `len` inside the last 16-byte vector came from the (padded) source: clear them so
@@ -550,7 +644,74 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     __syncthreads();
 
     MF_PHASE(3);
-    // ---- pass 3: Huffman codes, block header
+    // ---- pass 3a: price this chunk's symbols with the code lengths already in shared memory (previous chunk of the
+    // group) and against the entropy bound of its own histogram.  Integer sums only: the verdict must not depend
+    // on the order of the atomics.  Symbols 0..285 on warps 0..8, distance symbols on warp 9.
+    if (tid < 320) {
+        uint32_t h = 0, l = 0;
+        if (warp < 9) { if (tid < 286) { h = S.ll_hist[tid]; l = S.ll_lens[tid]; } }
+        else if (tid - 288u < 30u) { h = S.d_hist[tid - 288u]; l = S.d_lens[tid - 288u]; }
+        const uint32_t miss = __ballot_sync(0xFFFFFFFFu, h != 0 && l == 0);
+        const uint32_t cost = mf_warp_sum(h * l), a = mf_warp_sum(h);
+        const uint32_t bb = mf_warp_sum(h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u);
+        if (lane == 0) {
+            atomicAdd(&S.dec_cost, cost);
+            if (miss) atomicOr(&S.dec_miss, 1u);
+            if (warp < 9) { atomicAdd(&S.dec_a_ll, a); atomicAdd(&S.dec_b_ll, bb); }
+            else { atomicAdd(&S.dec_a_d, a); atomicAdd(&S.dec_b_d, bb); }
+        }
+    }
+    __syncthreads();
+    // entropy bound of the chunk's two histograms, in bits * 16 (every thread computes the same value)
+    float e16 = 0.f;
+    { const uint32_t a = S.dec_a_ll, bsum = S.dec_b_ll; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
+    { const uint32_t a = S.dec_a_d, bsum = S.dec_b_d; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
+    e16 = fmaxf(e16, 0.f);
+    const float nsym = (float)(S.dec_a_ll + S.dec_a_d);
+    const uint32_t cached_hb = S.cache_hdr_bits;
+    const bool reuse = cached_hb != 0 && S.dec_miss == 0 &&
+                       (float)S.dec_cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / 128.f) + 1024.f;
+    uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
+    if (reuse) {
+        // ---- pass 3 (codes kept): all warps zero region B (dead as hash tables now) and take one 64-byte CRC piece
+        // per thread; then the cached header is copied and the bits are counted with the cached code lengths
+        uint4 *z = reinterpret_cast<uint4 *>(S.regionB);
+        for (uint32_t i = tid; i < MF_REGION_B / 16; i += MF_ENC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+        uint32_t acc = 0;
+        {
+            const uint32_t start = tid * 64u;
+            if (start < len) {
+                const uint32_t end = min(start + 64u, len);
+                const uint32_t nw = (end - start) & ~3u;
+                uint32_t crc = mf_crc_words(S.data, start, nw, S.crc_tab);
+                for (uint32_t p = start + nw; p < end; p++) crc = S.crc_tab[0][(crc ^ S.data[p]) & 0xFFu] ^ (crc >> 8);
+                const uint32_t mul = (len == MF_CHUNK) ? g_mf_piece_mul[511u - tid] : mf_xpow8(len - end);
+                acc = mf_gf2_mul(crc, mul);
+            }
+        }
+        acc = mf_warp_xor(acc);
+        if (lane == 0) S.crc_part[warp] = acc;
+        MF_PHASE(8);
+        __syncthreads();
+        MF_PHASE(9); MF_PHASE(14); MF_PHASE(15); MF_PHASE(10); MF_PHASE(11); MF_PHASE(12);
+        if (warp == 0) {
+            for (uint32_t i = lane; i < ((cached_hb + 31u) >> 5); i += 32) outw[i] = S.hdr_cache[i];
+            if (lane == 0) S.hdr_bits = cached_hb;
+        }
+        for (uint32_t si = 0; si < 2; si++) {
+            const uint32_t seg = warp * 2 + si;
+            const uint32_t base = seg * MF_SEG;
+            uint32_t bits = 0;
+            if (base < len) {
+                const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
+                bits = mf_lane_emit_dev<false>(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.ll_lens, S.d_codes, nullptr);
+            }
+            S.lane_bits[seg][lane] = (uint16_t)bits;
+            uint32_t incl = mf_warp_incl_scan(bits, lane);
+            if (lane == 31) S.seg_bits[seg] = incl;
+        }
+    } else {
+    // ---- pass 3 (fresh codes): Huffman codes, block header
     // warp 0: literal/length code; warp 1: distance code (warp-synchronous, in registers); warps 2..15 meanwhile
     // zero region B (dead as hash tables now) for the bit writers and compute the chunk's CRC-32
     // (64-byte piece per lane, slice-by-4 tables in smem, GF(2) shift to the piece's position, xor-reduce).
@@ -579,22 +740,33 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     MF_PHASE(9);
     // warp 0: the block header (needs both codes); warps 1..15: bit counts per lane and per segment (need only
     // the code lengths), so the header's serial latency hides behind the counting
-    uint32_t *outw = reinterpret_cast<uint32_t *>(S.regionB);
     if (warp == 0) {
         uint32_t hb = mf_header_warp(S.ll_lens, S.d_lens, outw, S.whdr, lane, phase_clk ? &phase_clk[(size_t)c * 16 + 10] : nullptr);
         if (lane == 0) S.hdr_bits = hb;
+        // keep the header and the redundancy of these codes on their own chunk for the next chunk of the group
+        uint32_t own = 0;
+        for (uint32_t k = lane; k < 286u; k += 32) own += S.ll_hist[k] * S.ll_lens[k];
+        if (lane < 30) own += S.d_hist[lane] * S.d_lens[lane];
+        own = mf_warp_sum(own);
+        const bool fits = hb <= MF_HDR_CACHE_WORDS * 32u;
+        if (fits) for (uint32_t i = lane; i < ((hb + 31u) >> 5); i += 32) S.hdr_cache[i] = outw[i];
+        if (lane == 0) {
+            S.cache_hdr_bits = fits ? hb : 0u;
+            S.cache_red16 = nsym > 0.f ? fmaxf((float)own * 16.f - e16, 0.f) / nsym : 0.f;
+        }
     } else {
         for (uint32_t seg = warp - 1; seg < MF_SEGS_PER_CHUNK; seg += MF_ENC_WARPS - 1) {
             const uint32_t base = seg * MF_SEG;
             uint32_t bits = 0;
             if (base < len) {
                 const uint32_t seglen = min((uint32_t)MF_SEG, len - base);
-                bits = mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, nullptr);
+                bits = mf_lane_emit_dev<false>(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.ll_lens, S.d_codes, nullptr);
             }
             S.lane_bits[seg][lane] = (uint16_t)bits;
             uint32_t incl = mf_warp_incl_scan(bits, lane);
             if (lane == 31) S.seg_bits[seg] = incl;
         }
+    }
     }
     MF_PHASE(13);
     __syncthreads();
@@ -628,7 +800,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
             if (bits) {
                 MfBitWriter bw;
                 bw.init(outw, S.seg_off[seg] + incl - bits);
-                mf_lane_emit(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.d_codes, &bw);
+                mf_lane_emit_dev<true>(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.ll_lens, S.d_codes, &bw);
                 bw.flush();
             }
         }
@@ -677,6 +849,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
     }
     MF_PHASE(7);
     __syncthreads();          // shared memory is reused by the next chunk
+    }
     }
 #undef MF_PHASE
 }

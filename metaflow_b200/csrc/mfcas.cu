@@ -264,12 +264,14 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
         for (uint64_t i = 0; i < n; i++) { n_members += mf_n_members(src_len[i]); n_chunks += mf_n_chunks(src_len[i]); }
+    const uint64_t max_groups = n_chunks / MF_ENC_GROUP + n_members;      // encoder work units: <= 16 chunks of one member
     if (n_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
     Carver hc;
     const size_t o_hash = hc.take(sizeof(MfHashDesc) * n);
     const size_t o_blob = hc.take(sizeof(MfEncBlob) * n);
     const size_t o_mem = hc.take(sizeof(MfEncMember) * n_members);
     const size_t o_cm = hc.take(sizeof(uint32_t) * n_chunks);
+    const size_t o_grp = hc.take(sizeof(uint32_t) * max_groups);
     const size_t desc_bytes = hc.take(0);
     CU(W.h_desc.ensure(desc_bytes));
     CU(W.d_desc.ensure(desc_bytes));
@@ -278,6 +280,8 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
     MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
     uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
+    uint32_t *h_grp = reinterpret_cast<uint32_t *>(hd + o_grp);
+    uint32_t n_groups = 0;
     if (chain) {
         memcpy(h_hash, chain, sizeof(MfHashDesc) * n);
     } else {   // SHA-1 streams sorted by length (descending): the 32 streams of a CTA then finish together
@@ -311,6 +315,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
                 M.n_chunks = (uint32_t)mf_n_chunks(rl);
                 M.first_chunk = ci;
                 M.blob = (uint32_t)i;
+                for (uint32_t k = 0; k < M.n_chunks; k += MF_ENC_GROUP) h_grp[n_groups++] = ci + k;
                 for (uint32_t k = 0; k < M.n_chunks; k++) h_cm[ci++] = mi;
                 mi++;
             }
@@ -391,10 +396,11 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             unsigned sha_slots = 0;           // exclusive SHA-1 CTAs of this wave and of the waves still in flight
             for (WaveCtx &O : D.ring) if ((&O == &W || O.state == 1) && O.sha_excl) sha_slots += O.sha_ctas;
             const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, std::min(MF_ENC_GRID_CAP, MF_SM_SLOTS - std::min(sha_slots, MF_SM_SLOTS)));
-            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_chunks, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
+            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_groups, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
-                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket));
+                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket),
+                reinterpret_cast<const uint32_t *>(dd + o_grp), n_groups);
             CU(cudaGetLastError());
             D.launches++;
         }

@@ -119,6 +119,33 @@ def test_distributions_and_ratio(gpu_codec):
     assert ratios["zeros"] < 0.02 and ratios["lowent"] < 0.32 and ratios["text"] < 0.6
 
 
+def test_codes_carried_inside_a_group(gpu_codec):
+    """The encoder keeps the Huffman codes of the previous chunk of a 16-chunk group while they stay within 1/128 of
+    fresh ones.  Mix chunk kinds inside groups (stationary noise, sudden switches, symbols the kept code does not
+    cover, incompressible and empty-ish chunks): every stream must stay valid for zlib and for our decoder, packed
+    bytes must not depend on the batch around a blob, and the kept codes must not cost ratio on stationary data."""
+    rng = np.random.default_rng(23)
+    K = 32768
+    noise = lambda n: rng.standard_normal(n // 4, dtype=np.float32).tobytes()
+    text = (open(gzip.__file__, "rb").read() * 8)
+    kinds = [
+        noise(40 * K),                                                           # stationary: codes reused
+        b"".join(noise(K) if i % 2 else text[i * K:(i + 1) * K] for i in range(40)),   # alternating every chunk
+        noise(5 * K) + bytes(3 * K) + noise(5 * K) + bytes(range(256)) * 512 + noise(3 * K + 777),
+        b"".join(rng.integers(0, 1 << (1 + i % 8), K, dtype=np.uint8).tobytes() for i in range(37)),   # alphabet grows and shrinks
+        rng.integers(0, 256, 20 * K + 5, dtype=np.uint8).tobytes(),             # incompressible: stored chunks
+        bytes(17 * K) + b"x",
+    ]
+    _, packed = _roundtrip(gpu_codec, kinds)
+    # a blob's packed bytes are a function of the blob alone
+    _, alone = gpu_codec.pack_batch([kinds[1]])
+    assert bytes(alone[0]) == packed[1]
+    _, again = gpu_codec.pack_batch(list(reversed(kinds)))
+    assert [bytes(p) for p in reversed(again)] == packed
+    ratio = len(packed[0]) / len(kinds[0])
+    assert ratio <= len(gzip.compress(kinds[0], 1)) / len(kinds[0]) * 1.005, ratio
+
+
 def test_member_boundaries(gpu_codec):
     rng = np.random.default_rng(3)
     n = 768 * 32768
