@@ -381,6 +381,26 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
     return base;      // header length in bits
 }
 
+// 32-bit form of MfBitWriter for the device sweeps (same bits: LSB first, first word OR-ed, rest stored).
+struct MfBitWriterDev {
+    uint32_t *out;
+    uint32_t wi, acc, nacc;
+    bool first;
+    __device__ __forceinline__ void init(uint32_t *o, uint32_t bitpos) { out = o; wi = bitpos >> 5; acc = 0; nacc = bitpos & 31u; first = true; }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t nbits) {      // nbits <= 32, v < 2^nbits
+        acc |= v << nacc;
+        uint32_t n2 = nacc + nbits;
+        if (n2 >= 32u) {
+            if (first) { atomicOr(&out[wi], acc); first = false; } else out[wi] = acc;
+            wi++;
+            acc = __funnelshift_l(v, 0u, nacc);          // the bits of v that did not fit: v >> (32 - nacc), 0 when nacc == 0
+            n2 -= 32u;
+        }
+        nacc = n2;
+    }
+    __device__ __forceinline__ void flush() { if (nacc) atomicOr(&out[wi], acc); }
+};
+
 // Device form of mf_lane_emit (mf_core.h keeps the portable one for the CPU model): same tokens, same bits.
 // The portable loop reads the segment a byte at a time at a 32-byte lane stride -- an 8-way bank conflict per
 // read, twice per chunk, which made the two sweeps the shared-memory bottleneck of the encoder.  Here a lane
@@ -389,7 +409,7 @@ __device__ __forceinline__ uint32_t mf_header_warp(const uint8_t *ll_lens, const
 template <bool WRITE>
 __device__ __forceinline__ uint32_t mf_lane_emit_dev(const uint8_t *seg, uint32_t seglen, const uint32_t *matches, uint32_t nmatch,
                                                      uint32_t lane, const uint32_t *ll_codes, const uint8_t *ll_lens,
-                                                     const uint32_t *d_codes, MfBitWriter *w) {
+                                                     const uint32_t *d_codes, MfBitWriterDev *w) {
     const uint32_t lo = lane * 32u;
     const uint32_t hi = min(lo + 32u, seglen);
     if (lo >= hi) return 0;
@@ -516,6 +536,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
         const MfEncMember mem = members[chunk_member[c0]];
         const uint32_t c1 = min(c0 + MF_ENC_GROUP, mem.first_chunk + mem.n_chunks);
         if (tid == 0) S.cache_hdr_bits = 0;
+        uint32_t dry = 0;                        // consecutive probed windows of this warp that produced no match
     for (uint32_t c = c0; c < c1; c++) {
     // optional phase profile (MFCAS_PHASE_TIMING=1): clock64 at every phase boundary of thread 0
 #define MF_PHASE(k) do { if (phase_clk && tid == 0) phase_clk[(size_t)c * 16 + (k)] = clock64(); } while (0)
@@ -558,15 +579,19 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
             uint32_t nm = 0;
             uint32_t *ml = S.match[seg];
             uint32_t pos = 0;
-            uint32_t dry = 0;                    // consecutive probed windows that produced no match
             while (pos < seglen) {
                 const uint32_t p = pos + lane;
                 const bool valid = p < seglen;
-                // incompressible stretches (float noise): after 3 dry windows only every 4th window is probed,
-                // the others just feed the literal histogram (LZ4-style acceleration)
-                if (!lz || (dry >= 3 && ((pos >> 5) & 3u) != 0)) {
-                    if (valid) atomicAdd(&S.ll_hist[S.data[base + p]], 1u);
-                    pos += 32;
+                // incompressible stretches (float noise): the longer nothing matched, the fewer windows are probed --
+                // every 4th after 3 dry windows, every 8th after 6, every 16th after 12 (LZ4-style acceleration);
+                // the rest only feed the literal histogram.  `dry` is carried across this warp's segments and
+                // across the chunks of the group: a probed window costs ~80 instructions, a skipped one ~4.
+                const uint32_t stride = dry >= 12u ? 512u : dry >= 6u ? 256u : 128u;
+                if (!lz || (dry >= 3u && (pos & (stride - 32u)) != 0)) {
+                    // all literals up to the next probed window, in one step
+                    const uint32_t stop = lz ? min(seglen, (pos + stride) & ~(stride - 1u)) : seglen;
+                    for (uint32_t q = p; q < stop; q += 32) atomicAdd(&S.ll_hist[S.data[base + q]], 1u);
+                    pos = stop;
                     continue;
                 }
                 const uint32_t nm_before = nm;
@@ -798,7 +823,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
             uint32_t bits = S.lane_bits[seg][lane];
             uint32_t incl = mf_warp_incl_scan(bits, lane);
             if (bits) {
-                MfBitWriter bw;
+                MfBitWriterDev bw;
                 bw.init(outw, S.seg_off[seg] + incl - bits);
                 mf_lane_emit_dev<true>(S.data + base, seglen, S.match[seg], S.nmatch[seg], lane, S.ll_codes, S.ll_lens, S.d_codes, &bw);
                 bw.flush();

@@ -75,7 +75,7 @@ struct WaveCtx {
     int state = 0;                       // 0 idle, 1 kernels in flight, 2 output D2H in flight
     Op op = Op::Pack;
     uint64_t n = 0, n_chunks = 0;
-    unsigned sha_ctas = 0; bool sha_excl = false;
+    unsigned sha_ctas = 0;
     size_t r_len = 0, r_st = 0, r_sha = 0, res_bytes = 0;
     bool timed_pack = false;
     size_t pos = 0, wn = 0;              // slice [pos, pos+wn) of the shard (host-pointer API)
@@ -129,12 +129,11 @@ struct Carver {
 };
 
 #define MF_RING 8
-// Encoder CTAs resident at once.  An SM holds two 100+ KB CTAs -- encoder or SHA-1 (which asks for 112 KB so that
-// nothing else shares its schedulers).  The persistent encoder grid is sized to leave one such slot per SHA-1 CTA
-// that may be running beside it; otherwise whichever kernel's CTAs are dispatched first owns the SMs and the hash
-// chain (the longest pole of a wave) waits for the whole encoder.
+// Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
+// takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
+// otherwise whichever kernel's CTAs are dispatched first owns the SMs and the hash chain (the longest pole of a
+// wave) waits for the whole encoder.
 #define MF_SM_SLOTS (2u * 148u)
-#define MF_ENC_GRID_CAP 272u
 #define MF_ENC_GRID_MIN 168u
 
 int wave_setup(DeviceState &D, WaveCtx &W) {
@@ -158,7 +157,7 @@ int device_setup(DeviceState &D) {
     CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
-    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_SHA_UNITS * sizeof(MfShaSmem))));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
@@ -356,15 +355,15 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_in, s));
     }
     // Device-resident packing is ONE wave: a hash kernel that runs as long as its longest blob beside one long
-    // persistent encoder.  Which of the two is dispatched first decides whether the hash CTAs get SMs of their own
-    // (two 112 KB CTAs fill an SM) or share schedulers with encoder warps (13 % slower chain).  Make it
-    // deterministic: the encoder's stream waits (cuStreamWaitValue32) until every hash CTA has reported in.
+    // persistent encoder.  A SHA-1 CTA needs an SM of its own (216 KB of shared memory); if the encoder's CTAs are
+    // dispatched first they sit on every SM until the encoder is done and the hash chain -- the longest pole --
+    // starts late.  Make it deterministic: the encoder's stream waits (cuStreamWaitValue32) until every hash CTA
+    // has reported in.  (Host-pointer waves are short and many; there the encoder just leaves SMs free, below.)
     static const StreamWaitValue32Fn wait_value = stream_wait_value_fn();
     uint32_t *gate = nullptr;
-    const unsigned sha_spc = 32u;             // streams per CTA (measured: half-filled warps are no faster per stream)
-    const unsigned sha_ctas = (unsigned)((n + sha_spc - 1) / sha_spc);
-    const size_t sha_smem = sha_ctas <= 2 * 148 ? (size_t)112 * 1024 : sizeof(MfShaSmem);
-    if (!upload && !chain && want_pack && sha_smem > sizeof(MfShaSmem) && sha_ctas <= 64 && wait_value) {
+    const unsigned sha_ctas = (unsigned)((n + MF_SHA_STREAMS_PER_CTA - 1) / MF_SHA_STREAMS_PER_CTA);
+    const size_t sha_smem = MF_SHA_UNITS * sizeof(MfShaSmem);
+    if (!upload && !chain && want_pack && sha_ctas <= 32 && wait_value) {
         CU(D.gate.ensure(256));
         gate = D.gate.as<uint32_t>();
         CU(cudaMemsetAsync(gate, 0, sizeof(uint32_t), s));          // before ev_in: both kernels' streams wait on it
@@ -374,28 +373,25 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     CU(cudaStreamWaitEvent(s2, W.ev_in, 0));
     if (sha_deps) for (cudaEvent_t e : *sha_deps) CU(cudaStreamWaitEvent(s2, e, 0));   // earlier pieces of these blobs
     CU(cudaEventRecord(W.ev[0], s2));
-    // Few SHA CTAs (few, long streams): latency of the serial chain is everything, so keep other kernels'
-    // warps off their schedulers -- ask for enough shared memory that exactly two SHA CTAs (4 warps, one per
-    // SM sub-partition) own an SM.  Many CTAs (many short streams): throughput-bound, pack them densely.
     unsigned long long *sha_dbg = nullptr;
-    if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
-    W.sha_ctas = sha_ctas; W.sha_excl = sha_smem > sizeof(MfShaSmem);
-    mf_sha1_kernel<<<sha_ctas, 96, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, sha_spc, gate);
+    if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * MF_SHA_UNITS * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
+    W.sha_ctas = sha_ctas;
+    mf_sha1_kernel<<<sha_ctas, MF_SHA_THREADS, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, gate);
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(W.ev[1], s2));
     CU(cudaEventRecord(W.ev_sha, s2));
     if (want_pack) {
-        cudaStream_t sc = D.compute;          // one encoder kernel at a time per device (see MF_ENC_GRID_CAP)
+        cudaStream_t sc = D.compute;          // one encoder kernel at a time per device (its grid leaves the SHA-1 SMs free)
         CU(cudaStreamWaitEvent(sc, W.ev_in, 0));
         if (gate && wait_value((CUstream)sc, (CUdeviceptr)(uintptr_t)gate, sha_ctas, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS) {
             D.err = "cuStreamWaitValue32 failed"; return MFCAS_E_CUDA;
         }
         CU(cudaEventRecord(W.ev[2], sc));
         if (n_chunks) {
-            unsigned sha_slots = 0;           // exclusive SHA-1 CTAs of this wave and of the waves still in flight
-            for (WaveCtx &O : D.ring) if ((&O == &W || O.state == 1) && O.sha_excl) sha_slots += O.sha_ctas;
-            const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, std::min(MF_ENC_GRID_CAP, MF_SM_SLOTS - std::min(sha_slots, MF_SM_SLOTS)));
+            unsigned sha_sms = 0;             // SMs owned by SHA-1 CTAs of this wave and of the waves still in flight
+            for (WaveCtx &O : D.ring) if (&O == &W || O.state == 1) sha_sms += O.sha_ctas;
+            const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, MF_SM_SLOTS - 2u * std::min(sha_sms, 148u));
             mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_groups, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
                 reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
                 W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
@@ -451,12 +447,13 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
     cudaEventElapsedTime(&D.ms[0], W.ev[0], W.ev[1]);
     if (phase_timing_on()) {
         if (W.phase2.p) {
-            std::vector<unsigned long long> h((size_t)W.sha_ctas * 4);
+            const unsigned nu = W.sha_ctas * MF_SHA_UNITS;
+            std::vector<unsigned long long> h((size_t)nu * 4);
             CU(cudaMemcpy(h.data(), W.phase2.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             double a[4] = {0};
-            for (unsigned c = 0; c < W.sha_ctas; c++) for (int k = 0; k < 4; k++) a[k] += (double)h[c * 4 + k];
-            fprintf(stderr, "[mfcas phase] sha1 over %u CTAs: producer wait=%.0f total=%.0f | consumer wait=%.0f total=%.0f cycles\n", W.sha_ctas,
-                    a[0] / W.sha_ctas, a[1] / W.sha_ctas, a[2] / W.sha_ctas, a[3] / W.sha_ctas);
+            for (unsigned c = 0; c < nu; c++) for (int k = 0; k < 4; k++) a[k] += (double)h[c * 4 + k];
+            fprintf(stderr, "[mfcas phase] sha1 over %u units: producer wait=%.0f total=%.0f | consumer wait=%.0f total=%.0f cycles\n", nu,
+                    a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu);
         }
         if (W.timed_pack && W.n_chunks && W.phase.p) {
             const uint64_t nc = W.n_chunks;
