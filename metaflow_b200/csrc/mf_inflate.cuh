@@ -137,6 +137,7 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
 
 // ------------------------------------------------------------------ chunk decoder
 #define MF_DEC_WARPS 8
+#define MF_DEC_GROUP 16u      // consecutive chunks per warp (header/LUT reuse)
 #define MF_LL_LUT_BITS 10
 #define MF_D_LUT_BITS 8
 
@@ -268,9 +269,18 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
     __syncthreads();
-    const uint32_t c = blockIdx.x * MF_DEC_WARPS + warp;
-    if (c >= counters->n_chunks) return;
+    // A warp takes MF_DEC_GROUP consecutive chunks.  The encoder repeats a block header verbatim while the codes
+    // of a group stay good, and parsing it (one lane, ~316 code lengths) plus building the LUTs costs almost half
+    // of what decoding the chunk's 32 segments does: when a chunk's header equals the previous chunk's bit for
+    // bit, the tables in shared memory are simply kept.
+    const uint32_t n_chunks = counters->n_chunks;
+    const uint32_t c0 = (blockIdx.x * MF_DEC_WARPS + warp) * MF_DEC_GROUP;
+    if (c0 >= n_chunks) return;
+    const uint32_t c1 = min(c0 + MF_DEC_GROUP, n_chunks);
     MfDecWarpSmem &W = S.w[warp];
+    const uint8_t *tab_src = nullptr;      // header the tables in W were built from (null: none)
+    uint32_t tab_bits = 0;
+    for (uint32_t c = c0; c < c1; c++) {
     const MfDecChunk ch = chunks[c];
     const uint32_t raw_len = ch.raw_len;
     const uint32_t seg_base = lane * MF_SEG;
@@ -295,6 +305,17 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
             crc = wr.finish(S.crc_tab);
         }
     } else {
+        // same header as the chunk the tables came from?  (whole bytes + the low bits of the last one)
+        bool same = false;
+        if (tab_src != nullptr && ch.hdr_bits == tab_bits && (uint64_t)ch.comp_bytes * 8ull >= ch.hdr_bits) {
+            const uint32_t nby = tab_bits >> 3, rem = tab_bits & 7u;
+            bool diff = false;
+            for (uint32_t k = lane; k < nby; k += 32) diff |= (ch.src[k] != tab_src[k]);
+            if (lane == 0 && rem) diff |= (((uint32_t)ch.src[nby] ^ (uint32_t)tab_src[nby]) & ((1u << rem) - 1u)) != 0;
+            same = !__any_sync(0xFFFFFFFFu, diff);
+        }
+        if (!same) {
+        tab_src = nullptr;
         // ---- block header (lane 0), lengths into smem
         if (lane == 0) {
             MfBitReader br; br.init(ch.src, ch.comp_bytes, 0);
@@ -374,6 +395,10 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                 }
             }
             __syncwarp();
+            tab_src = ch.src; tab_bits = ch.hdr_bits;
+        }
+        }
+        if (!err) {
             // ---- 32 lanes decode 32 segments
             const uint32_t mybits = mf_le16(ch.segidx + 2u * lane);
             const uint32_t incl = mf_warp_incl_scan(mybits, lane);
@@ -413,7 +438,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
         }
         __syncwarp();
     }
-    if (err) { if (lane == 0) { mf_set_status(status, ch.blob, err); chunk_crc[c] = 0; } return; }
+    if (err) { if (lane == 0) { mf_set_status(status, ch.blob, err); chunk_crc[c] = 0; } continue; }
 
     // ---- chunk CRC: every lane's segment CRC shifted by the bytes that follow it, xor-reduced
     if (seglen) {
@@ -423,6 +448,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     }
     crc = mf_warp_xor(crc);
     if (lane == 0) chunk_crc[c] = crc;
+    }
 }
 
 __global__ void __launch_bounds__(128)

@@ -523,7 +523,7 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
                                                reinterpret_cast<MfDecMember *>(dw + o_members), (uint32_t)max_members, cnt,
                                                dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
-    mf_inflate_chunk_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS - 1) / MF_DEC_WARPS), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
+    mf_inflate_chunk_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS * MF_DEC_GROUP - 1) / (MF_DEC_WARPS * MF_DEC_GROUP)), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
         reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
     CU(cudaEventRecord(W.ev[6], s));
