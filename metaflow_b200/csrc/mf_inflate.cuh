@@ -410,12 +410,43 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                 MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
                 while (wr.op < seglen) {
                     if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
-                    br.fill();
-                    uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
-                    int sym;
-                    if (e) { sym = (int)(e & 511u); br.drop(e >> 9); }
-                    else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
-                    if (sym < 256) { wr.put((uint32_t)sym, S.crc_tab); continue; }
+                    int sym = -2;
+                    if (wr.vec && (wr.op & 15u) == 0 && wr.op + 16u <= seglen) {
+                        // Fast path: the next 16 output bytes start a 16-byte window and are (usually) all literals.
+                        // Unrolled, so byte and word positions are static: no shift/select arithmetic on the writer,
+                        // one CRC fold per word, one 16-byte store.  A length symbol leaves the loop with the writer
+                        // state exact (op, cw, w[]) and is handled below.  (At most 16 x 15 bits are consumed before
+                        // the bound on `used` is checked again; the reader itself never leaves the blob.)
+#pragma unroll
+                        for (int k = 0; k < 16; k++) {
+                            br.fill();
+                            const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
+                            int s2;
+                            if (e) { s2 = (int)(e & 511u); br.drop(e >> 9); }
+                            else s2 = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol);
+                            if (s2 >= 256 || s2 < 0) { sym = s2; break; }
+                            wr.cw |= (uint32_t)s2 << (8 * (k & 3));
+                            wr.op++;
+                            if ((k & 3) == 3) {
+                                const uint32_t x = wr.crc ^ wr.cw;
+                                wr.crc = S.crc_tab[3][x & 0xFFu] ^ S.crc_tab[2][(x >> 8) & 0xFFu] ^ S.crc_tab[1][(x >> 16) & 0xFFu] ^ S.crc_tab[0][x >> 24];
+                                wr.w[k >> 2] = wr.cw;
+                                wr.cw = 0;
+                            }
+                        }
+                        if (sym == -2) {       // all 16 were literals
+                            *reinterpret_cast<uint4 *>(wr.dst + wr.op - 16) = make_uint4(wr.w[0], wr.w[1], wr.w[2], wr.w[3]);
+                            wr.w[0] = wr.w[1] = wr.w[2] = wr.w[3] = 0;
+                            continue;
+                        }
+                        if (sym < 0) { lerr = MF_DEC_E_STREAM; break; }
+                    } else {
+                        br.fill();
+                        uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
+                        if (e) { sym = (int)(e & 511u); br.drop(e >> 9); }
+                        else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
+                        if (sym < 256) { wr.put((uint32_t)sym, S.crc_tab); continue; }
+                    }
                     if (sym == 256 || sym > 285) { lerr = MF_DEC_E_STREAM; break; }
                     br.fill();
                     sym -= 257;
