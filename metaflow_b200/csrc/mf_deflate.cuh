@@ -601,7 +601,7 @@ mf_deflate_kernel(const MfEncMember *__restrict__ members, const uint32_t *__res
                 int q = -1;
                 if (can) { uint32_t cnd = ht[h]; if (cnd) q = (int)cnd - 1; }
                 __syncwarp();
-                if (can) ht[h] = (uint16_t)(p + 1);
+                if (can) ht[h] = (uint16_t)(p + 1);      // lanes with equal hashes write the same slot: whichever lands is a valid candidate (racecheck flags it)
                 __syncwarp();
                 // in-window probes (the hash table only knows earlier windows)
                 {
