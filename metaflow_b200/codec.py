@@ -158,35 +158,51 @@ class GpuCodec(object):
             raise DataException("GPU codec call failed (%s): %s" % (
                 capi.STATUS_TEXT.get(rc, rc), self._lib.mfcas_last_error(self._ctx).decode("utf-8", "replace")))
 
+    @staticmethod
+    def _slots(sizes):
+        """sizes (uint64 array) -> (offsets, total): 256-byte aligned slots with a 256-byte gap, vectorised."""
+        step = (sizes + np.uint64(_ALIGN - 1)) // np.uint64(_ALIGN) * np.uint64(_ALIGN) + np.uint64(_ALIGN)
+        ends = np.cumsum(step, dtype=np.uint64)
+        return (ends - step).astype(np.uint64), int(ends[-1]) if len(ends) else 0
+
     def _stage_inputs(self, blobs):
         n = len(blobs)
         lens = np.fromiter((len(b) for b in blobs), dtype=np.uint64, count=n)
-        offs = np.zeros(n, dtype=np.uint64)
-        total = 0
-        for i in range(n):
-            offs[i] = total
-            total += _align(int(lens[i])) + _ALIGN
+        offs, total = self._slots(lens)
         self._in.ensure(total + _ALIGN)
         arr = self._in.arr
+        lens_l, offs_l = lens.tolist(), offs.tolist()
 
-        def stage(i):
-            ln = int(lens[i])
-            if ln:
-                o = int(offs[i])
-                b = blobs[i]
-                if isinstance(b, Segments):
-                    b.copy_into(arr, o)                # pickle stream pieces + the arrays' own buffers
-                elif isinstance(b, FileSource):
-                    b.read_into(arr, o)                # file -> page-locked memory, no bytes object in between
-                else:
-                    arr[o:o + ln] = _as_u8(b)          # numpy releases the GIL for large copies
+        def stage(lo, hi):
+            for i in range(lo, hi):
+                ln = lens_l[i]
+                if ln:
+                    o = offs_l[i]
+                    b = blobs[i]
+                    if isinstance(b, Segments):
+                        b.copy_into(arr, o)                # pickle stream pieces + the arrays' own buffers
+                    elif isinstance(b, FileSource):
+                        b.read_into(arr, o)                # file -> page-locked memory, no bytes object in between
+                    else:
+                        arr[o:o + ln] = _as_u8(b)          # numpy releases the GIL for large copies
 
         if n >= 4 and total >= (64 << 20):
-            with ThreadPoolExecutor(max_workers=8) as pool:
-                list(pool.map(stage, range(n)))
-        else:
+            # a few contiguous ranges of about equal bytes per worker (not one task per blob: a wide foreach of
+            # small artifacts is 65536 blobs)
+            workers = 8
+            target = total // (workers * 4) + 1
+            cuts, acc = [0], 0
             for i in range(n):
-                stage(i)
+                acc += lens_l[i]
+                if acc >= target:
+                    cuts.append(i + 1)
+                    acc = 0
+            if cuts[-1] != n:
+                cuts.append(n)
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                list(pool.map(lambda k: stage(cuts[k], cuts[k + 1]), range(len(cuts) - 1)))
+        else:
+            stage(0, n)
         src = (offs + np.uint64(self._in.base)).astype(np.uint64)
         return lens, src
 
@@ -222,16 +238,15 @@ class GpuCodec(object):
             return [], []
         lib = self._lib
         lens, src = self._stage_inputs(blobs)
-        counts = np.fromiter((lib.mfcas_pack_extent_count(int(x)) for x in lens), dtype=np.uint64, count=n)
-        caps = np.fromiter((lib.mfcas_pack_extent_bound(int(x)) for x in lens), dtype=np.uint64, count=n)
-        ooffs = np.zeros(n, dtype=np.uint64)
-        total = 0
-        for i in range(n):
-            ooffs[i] = total
-            total += _align(int(caps[i])) + _ALIGN
+        geo = {}                                   # a foreach's artifacts have few distinct lengths
+        for x in set(lens.tolist()):
+            geo[x] = (lib.mfcas_pack_extent_count(x), lib.mfcas_pack_extent_bound(x))
+        lens_l = lens.tolist()
+        counts = np.fromiter((geo[x][0] for x in lens_l), dtype=np.uint64, count=n)
+        caps = np.fromiter((geo[x][1] for x in lens_l), dtype=np.uint64, count=n)
+        ooffs, total = self._slots(caps)
         self._out.ensure(total + _ALIGN)
         dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
-        bases = np.concatenate(([0], np.cumsum(counts)[:-1])).astype(np.int64)
         n_ext = int(counts.sum())
         ext_off = np.zeros(n_ext, dtype=np.uint64)
         ext_len = np.zeros(n_ext, dtype=np.uint64)
@@ -246,10 +261,12 @@ class GpuCodec(object):
         raw = sha.tobytes()
         keys = [raw[20 * i:20 * i + 20].hex() for i in range(n)]
         mv = memoryview(self._out.arr)
-        packed = []
-        for i in range(n):
-            o, b = int(ooffs[i]), int(bases[i])
-            packed.append(Packed([mv[o + int(ext_off[b + k]):o + int(ext_off[b + k]) + int(ext_len[b + k])] for k in range(int(counts[i]))]))
+        starts = (np.repeat(ooffs, counts.astype(np.int64)) + ext_off).tolist()       # absolute start of every extent
+        ends = (np.repeat(ooffs, counts.astype(np.int64)) + ext_off + ext_len).tolist()
+        packed, k = [], 0
+        for c in counts.tolist():
+            packed.append(Packed([mv[starts[j]:ends[j]] for j in range(k, k + c)]))
+            k += c
         return keys, packed
 
     def pack_batch_contiguous(self, blobs):
@@ -258,12 +275,9 @@ class GpuCodec(object):
         if n == 0:
             return [], []
         lens, src = self._stage_inputs(blobs)
-        caps = np.fromiter((self._lib.mfcas_pack_bound(int(x)) for x in lens), dtype=np.uint64, count=n)
-        ooffs = np.zeros(n, dtype=np.uint64)
-        total = 0
-        for i in range(n):
-            ooffs[i] = total
-            total += _align(int(caps[i])) + _ALIGN
+        bound = {x: self._lib.mfcas_pack_bound(x) for x in set(lens.tolist())}
+        caps = np.fromiter((bound[x] for x in lens.tolist()), dtype=np.uint64, count=n)
+        ooffs, total = self._slots(caps)
         self._out.ensure(total + _ALIGN)
         dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
         dlen = np.zeros(n, dtype=np.uint64)
@@ -324,12 +338,8 @@ class GpuCodec(object):
             idx = np.array(todo, dtype=np.int64)
             lens, src = np.ascontiguousarray(all_lens[idx]), np.ascontiguousarray(all_src[idx])
             m = len(todo)
-            caps = np.array([int(sizes[i]) for i in todo], dtype=np.uint64)
-            ooffs = np.zeros(m, dtype=np.uint64)
-            total = 0
-            for k in range(m):
-                ooffs[k] = total
-                total += _align(int(caps[k])) + _ALIGN
+            caps = np.ascontiguousarray(sizes[idx])
+            ooffs, total = self._slots(caps)
             self._out.ensure(total + _ALIGN)
             dst = (ooffs + np.uint64(self._out.base)).astype(np.uint64)
             dlen = np.zeros(m, dtype=np.uint64)
@@ -338,14 +348,15 @@ class GpuCodec(object):
                                                      self._p64(dlen), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
             mv = memoryview(self._out.arr)
             retry = []
+            st_l, oo_l, dl_l = st.tolist(), ooffs.tolist(), dlen.tolist()
             for k, i in enumerate(todo):
-                code = int(st[k])
+                code = st_l[k]
                 if code == capi.OK:
-                    view = mv[int(ooffs[k]):int(ooffs[k]) + int(dlen[k])]
+                    view = mv[oo_l[k]:oo_l[k] + dl_l[k]]
                     results[i] = bytes(view) if (as_bytes or retry) else view
                 elif code == capi.E_DST_TOO_SMALL and attempt < 8:
                     # foreign multi-member / >4 GiB streams: the ISIZE hint was short -- grow and retry
-                    sizes[i] = max(int(dlen[k]), 2 * int(sizes[i]) + 65536)
+                    sizes[i] = max(dl_l[k], 2 * int(sizes[i]) + 65536)
                     retry.append(i)
                 else:
                     results[i] = UnpackError(code)
