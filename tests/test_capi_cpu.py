@@ -74,3 +74,36 @@ def test_product_never_imports_the_oracle():
                     text = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), os.path.join(root, fn)
                 assert not re.search(r"^\s*(from|import)\s+(zlib|gzip|hashlib)\b", text, re.M), os.path.join(root, fn)
+
+
+def test_codec_slot_layout_is_vectorised_and_aligned():
+    """GpuCodec._slots: 256-byte aligned slots with a 256-byte gap -- the layout the page-locked arenas use."""
+    import numpy as np
+    from metaflow_b200.codec import GpuCodec
+    sizes = np.array([0, 1, 255, 256, 257, 65697, 16777379], dtype=np.uint64)
+    offs, total = GpuCodec._slots(sizes)
+    assert offs.dtype == np.uint64 and offs[0] == 0
+    for i in range(len(sizes)):
+        assert int(offs[i]) % 256 == 0
+        end = int(offs[i]) + int(sizes[i])
+        nxt = int(offs[i + 1]) if i + 1 < len(sizes) else total
+        assert nxt - end >= 256 and nxt - end < 512 + 256
+    assert GpuCodec._slots(np.zeros(0, dtype=np.uint64))[1] == 0
+
+
+def test_file_source_reads_into_a_buffer(tmp_path):
+    import numpy as np
+    from metaflow_b200.codec import FileSource
+    data = bytes(range(256)) * 300
+    p = tmp_path / "blob"
+    p.write_bytes(data)
+    fs = FileSource(str(p), len(data))
+    dst = np.full(len(data) + 100, 0xAA, dtype=np.uint8)
+    fs.read_into(dst, 50)
+    assert dst[50:50 + len(data)].tobytes() == data and (dst[:50] == 0xAA).all() and (dst[50 + len(data):] == 0xAA).all()
+    assert len(fs) == len(data) and fs.head(10) == data[:10]
+    short = FileSource(str(p), len(data) + 5)          # the file is shorter than promised
+    import pytest
+    from metaflow_b200.exception import DataException
+    with pytest.raises(DataException):
+        short.read_into(np.zeros(len(data) + 5, dtype=np.uint8), 0)

@@ -359,3 +359,61 @@ def test_device_resident_api(gpu_codec):
     for i, b in enumerate(blobs):
         assert olen[i] == len(b) and d_out[i][: len(b)].cpu().numpy().tobytes() == b
     assert lib.mfcas_stream(gpu_codec._ctx, 0)
+
+
+def test_c_abi_contract_edges(gpu_codec):
+    """The raw C ABI: undersized destinations are reported per blob (and the other blobs of the batch are untouched by
+    it), empty batches and bad arguments return codes instead of crashing."""
+    from metaflow_b200 import capi
+    lib = capi.load()
+    ctx = gpu_codec._ctx
+    rng = np.random.default_rng(41)
+    blobs = [rng.standard_normal(700000, dtype=np.float32).tobytes(), b"tiny", rng.integers(0, 4, 3 << 20, dtype=np.uint8).tobytes()]
+    n = len(blobs)
+    u64, vp = ctypes.c_uint64, ctypes.c_void_p
+    src_buf = [ctypes.create_string_buffer(b, len(b)) for b in blobs]
+    src = (vp * n)(*[ctypes.addressof(s) for s in src_buf]); slen = (u64 * n)(*map(len, blobs))
+    st = (ctypes.c_int32 * n)(); sha = ctypes.create_string_buffer(20 * n)
+
+    # contiguous packer: blob 0 gets a destination that is too small
+    caps = [lib.mfcas_pack_bound(len(b)) for b in blobs]
+    caps[0] = 1000
+    dst_buf = [ctypes.create_string_buffer(c + 16) for c in caps]
+    dst = (vp * n)(*[ctypes.addressof(d) for d in dst_buf]); dcap = (u64 * n)(*caps); dlen = (u64 * n)()
+    assert lib.mfcas_pack_batch(ctx, n, src, slen, dst, dcap, dlen, sha, st) == capi.OK
+    assert list(st) == [capi.E_DST_TOO_SMALL, 0, 0] and dlen[0] > 1000          # the need is reported
+    assert sha.raw[:20] == hashlib.sha1(blobs[0]).digest()                       # the digest does not depend on the destination
+    for i in (1, 2):
+        assert gzip.decompress(dst_buf[i].raw[:dlen[i]]) == blobs[i]
+
+    # striped packer: same contract per blob
+    ecaps = [lib.mfcas_pack_extent_bound(len(b)) for b in blobs]
+    ecaps[2] -= 1
+    cnt = [lib.mfcas_pack_extent_count(len(b)) for b in blobs]
+    edst_buf = [ctypes.create_string_buffer(c + 16) for c in ecaps]
+    edst = (vp * n)(*[ctypes.addressof(d) for d in edst_buf]); ecap = (u64 * n)(*ecaps)
+    eo = (u64 * sum(cnt))(); el = (u64 * sum(cnt))()
+    assert lib.mfcas_pack_batch_extents(ctx, n, src, slen, edst, ecap, eo, el, sha, st) == capi.OK
+    assert list(st) == [0, 0, capi.E_DST_TOO_SMALL]
+    base = 0
+    for i in range(2):
+        z = b"".join(edst_buf[i].raw[eo[base + k]:eo[base + k] + el[base + k]] for k in range(cnt[i]))
+        assert gzip.decompress(z) == blobs[i]
+        base += cnt[i]
+
+    # unpack into an undersized destination
+    good = dst_buf[2].raw[:dlen[2]]
+    psrc_buf = ctypes.create_string_buffer(good, len(good))
+    psrc = (vp * 1)(ctypes.addressof(psrc_buf)); plen = (u64 * 1)(len(good))
+    out = ctypes.create_string_buffer(len(blobs[2]))
+    odst = (vp * 1)(ctypes.addressof(out)); ocap = (u64 * 1)(len(blobs[2]) - 1); olen = (u64 * 1)(); st1 = (ctypes.c_int32 * 1)()
+    assert lib.mfcas_unpack_batch(ctx, 1, psrc, plen, odst, ocap, olen, st1) == capi.OK
+    assert st1[0] == capi.E_DST_TOO_SMALL and olen[0] == len(blobs[2])
+    ocap[0] = len(blobs[2])
+    assert lib.mfcas_unpack_batch(ctx, 1, psrc, plen, odst, ocap, olen, st1) == capi.OK and st1[0] == 0 and out.raw == blobs[2]
+
+    # empty batch, null arguments
+    assert lib.mfcas_pack_batch(ctx, 0, None, None, None, None, None, None, None) == capi.OK
+    assert lib.mfcas_unpack_batch(ctx, 0, None, None, None, None, None, None) == capi.OK
+    assert lib.mfcas_pack_batch(ctx, 1, None, None, None, None, None, None, None) == capi.E_ARG
+    assert lib.mfcas_pack_batch(None, 1, src, slen, dst, dcap, dlen, sha, st) == capi.E_ARG
