@@ -37,3 +37,8 @@ GPU_CAS_WAVE_BYTES = from_conf("GPU_CAS_WAVE_BYTES", 1 << 30)  # bytes (in + out
 # blobs as the caller has (the page-locked staging arenas grow on demand up to in + out of this size).
 GPU_CAS_WINDOW_BYTES = from_conf("GPU_CAS_WINDOW_BYTES", 4 << 30)
 GPU_CAS_LZ = from_conf("GPU_CAS_LZ", 1)                        # 0 = Huffman-only encoder
+
+# client-side file cache (metaflow/metaflow_config.py:113-121)
+CLIENT_CACHE_PATH = from_conf("CLIENT_CACHE_PATH", "/tmp/metaflow_client")
+CLIENT_CACHE_MAX_SIZE = from_conf("CLIENT_CACHE_MAX_SIZE", 10000)                         # megabytes
+CLIENT_CACHE_MAX_FLOWDATASTORE_COUNT = from_conf("CLIENT_CACHE_MAX_FLOWDATASTORE_COUNT", 50)
