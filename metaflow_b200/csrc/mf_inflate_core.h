@@ -67,6 +67,35 @@ MF_HD int mf_canon_decode(MfBitReader &br, const MfCanon &h) {
     return -1;
 }
 
+// 9-bit first-level table beside the canonical one, for streams decoded by a single lane (reference-written
+// files have no index, so a whole blob is one serial stream): one lookup per symbol instead of a bit-by-bit walk
+// over up to 15 lengths, each step a dependent local-memory load.  entry = symbol | length << 9; 0 = longer code.
+#define MF_GEN_LUT_BITS 9
+struct MfCanonLut { uint16_t e[1u << MF_GEN_LUT_BITS]; };
+MF_HD void mf_canon_lut_build(MfCanonLut &t, const MfCanon &h, const uint8_t *len, int n) {
+    for (uint32_t i = 0; i < (1u << MF_GEN_LUT_BITS); i++) t.e[i] = 0;
+    uint32_t next[16];
+    uint32_t code = 0;
+    next[0] = 0;
+    for (int l = 1; l < 16; l++) { code = (code + (l > 1 ? h.count[l - 1] : 0)) << 1; next[l] = code; }
+    for (int s = 0; s < n; s++) {
+        const uint32_t l = len[s] & 15u;
+        if (!l) continue;
+        const uint32_t c = next[l]++;
+        if (l > MF_GEN_LUT_BITS) continue;
+        uint32_t rev = 0;
+        for (uint32_t k = 0; k < l; k++) rev |= ((c >> k) & 1u) << (l - 1 - k);
+        const uint16_t ent = (uint16_t)((uint32_t)s | (l << 9));
+        for (uint32_t k = rev; k < (1u << MF_GEN_LUT_BITS); k += (1u << l)) t.e[k] = ent;
+    }
+}
+MF_HD int mf_canon_decode_lut(MfBitReader &br, const MfCanon &h, const MfCanonLut &t) {
+    const uint32_t bits = br.peek(15);
+    const uint32_t ent = t.e[bits & ((1u << MF_GEN_LUT_BITS) - 1u)];
+    if (ent) { br.drop(ent >> 9); return br.over ? -1 : (int)(ent & 511u); }
+    return mf_canon_decode(br, h);
+}
+
 struct MfDeflateTables {
     uint16_t lbase[29]; uint8_t lext[29]; uint16_t dbase[30]; uint8_t dext[30];
 };
@@ -112,6 +141,7 @@ MF_HD int mf_inflate_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
     uint64_t op = 0;
     uint32_t last = 0;
     MfCanon ll, dd;
+    MfCanonLut lut;
     uint8_t lens[320];
     while (!last) {
         last = br.get(1);
@@ -139,6 +169,7 @@ MF_HD int mf_inflate_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
             for (; s < 280; s++) lens[s] = 7;
             for (; s < 288; s++) lens[s] = 8;
             mf_canon_build(ll, lens, 288);
+            mf_canon_lut_build(lut, ll, lens, 288);
             for (s = 0; s < 30; s++) lens[s] = 5;
             mf_canon_build(dd, lens, 30);
         } else {
@@ -147,11 +178,12 @@ MF_HD int mf_inflate_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64
             if (e) return e;
             int r = mf_canon_build(ll, lens, (int)hlit);
             if (r < 0 || (r > 0 && (int)hlit - ll.count[0] != 1)) return MF_DEC_E_STREAM;
+            mf_canon_lut_build(lut, ll, lens, (int)hlit);
             r = mf_canon_build(dd, lens + hlit, (int)hdist);
             if (r < 0 || (r > 0 && (int)hdist - dd.count[0] != 1)) return MF_DEC_E_STREAM;
         }
         for (;;) {
-            int sym = mf_canon_decode(br, ll);
+            int sym = mf_canon_decode_lut(br, ll, lut);
             if (sym < 0) return br.over ? MF_DEC_E_TRUNC : MF_DEC_E_STREAM;
             if (sym < 256) {
                 if (op >= cap) return MF_DEC_E_DST;
