@@ -67,6 +67,26 @@ def test_serial_inflater_on_zlib_streams():
     assert e == 0 and out == data
 
 
+def test_serial_inflater_long_codes_and_every_symbol():
+    """Streams whose literal/length codes are longer than the inflater's 9-bit first-level table (skewed
+    distributions give 10..15-bit codes to rare symbols) and that use long matches and far distances."""
+    rng = np.random.default_rng(77)
+    skew = rng.choice(256, size=300000, p=np.array([0.5 ** min(i + 1, 22) for i in range(256)]) / sum(0.5 ** min(i + 1, 22) for i in range(256))).astype(np.uint8).tobytes()
+    every = bytes(range(256)) * 40 + bytes(200000) + bytes(rng.integers(0, 256, 70000, dtype=np.uint8)) + (b"0123456789abcdef" * 4096)
+    text = (open(gzip.__file__, "rb").read() * 6)
+    for name, blob in (("skew", skew), ("every", every), ("text", text)):
+        for level in (1, 6, 9):
+            z = gzip.compress(blob, level)
+            e, out = model_lib.gunzip(z, len(blob))
+            assert e == 0 and out == blob, (name, level, e)
+            # truncated and bit-flipped streams are reported, never decoded to the wrong bytes silently
+            e, out = model_lib.gunzip(z[: len(z) // 2], len(blob))
+            assert e != 0
+            bad = bytearray(z); bad[len(z) // 2] ^= 0x10
+            e, out = model_lib.gunzip(bytes(bad), len(blob))
+            assert e != 0 or out != blob
+
+
 def test_multi_member_boundary():
     rng = np.random.default_rng(5)
     n = 768 * 32768                       # MF_MEMBER_RAW
