@@ -13,7 +13,7 @@
 //                            in on the way (no shared-memory staging: registers bound the occupancy)
 //   mf_verify_kernel         one warp per member: GF(2)-combine the chunk CRCs, compare with trailer
 //   mf_gunzip_lane_kernel    foreign streams (stock Metaflow / zlib level 3 writers): a DEFLATE stream
-//                            without an index is bit-serial, so one lane decodes one whole blob
+//                            without an index is bit-serial: one warp per blob, lane 0 decodes
 #pragma once
 #include <cuda_runtime.h>
 #include "mf_core.h"
@@ -498,15 +498,171 @@ mf_verify_kernel(const MfDecMember *__restrict__ members, const MfDecCounters *_
     if (lane == 0 && mf_crc_finish(acc, mem.raw_len) != mem.crc_expect) mf_set_status(status, mem.blob, MF_DEC_E_CRC);
 }
 
-// foreign streams: one lane per blob
+// ---- serial inflater of a whole (foreign) DEFLATE stream, device form.  Same logic as mf_inflate_stream
+// (mf_inflate_core.h, which stays the portable reference and handles the block headers here too), but the symbol
+// loop is the chunk decoder's: word-wise bit reader with lookahead, 10-bit / 8-bit first-level tables in shared
+// memory.  A lone lane hides no latency -- every dependent instruction costs its full 4+ cycles -- so what matters
+// is the length of the per-symbol chain: ~20 instructions here against ~65 in the portable loop.
+struct MfForeignSmem { MfInflateWork work; uint16_t lut_ll[1u << MF_LL_LUT_BITS]; uint16_t lut_d[1u << MF_D_LUT_BITS]; };
+
+__device__ void mf_luts_serial(const MfCanon &h, const uint8_t *len, int n, uint16_t *lut, uint32_t lut_bits, uint32_t len_shift) {
+    for (uint32_t i = 0; i < (1u << lut_bits); i++) lut[i] = 0;
+    uint32_t next[16];
+    uint32_t code = 0;
+    next[0] = 0;
+    for (int l = 1; l < 16; l++) { code = (code + (l > 1 ? h.count[l - 1] : 0)) << 1; next[l] = code; }
+    for (int s = 0; s < n; s++) {
+        const uint32_t l = len[s] & 15u;
+        if (!l) continue;
+        const uint32_t c = next[l]++;
+        if (l > lut_bits) continue;
+        const uint32_t rev = __brev(c) >> (32 - l);
+        const uint16_t ent = (uint16_t)((uint32_t)s | (l << len_shift));
+        for (uint32_t k = rev; k < (1u << lut_bits); k += (1u << l)) lut[k] = ent;
+    }
+}
+
+__device__ int mf_inflate_stream_dev(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *consumed, uint64_t *produced, MfForeignSmem &F) {
+    MfInflateWork &W = F.work;
+    uint64_t bitpos = 0, op = 0;
+    uint32_t last = 0;
+    while (!last) {
+        MfBitReader br; br.init(src, n, bitpos);
+        last = br.get(1);
+        const uint32_t type = br.get(2);
+        if (br.over) return MF_DEC_E_TRUNC;
+        if (type == 0) {
+            uint64_t bp = (br.bitpos() + 7ull) >> 3;          // skip to the byte boundary
+            if (bp + 4 > n) return MF_DEC_E_TRUNC;
+            const uint32_t len = src[bp] | ((uint32_t)src[bp + 1] << 8), nlen = src[bp + 2] | ((uint32_t)src[bp + 3] << 8);
+            if ((len ^ 0xFFFFu) != nlen) return MF_DEC_E_STREAM;
+            bp += 4;
+            if (bp + len > n) return MF_DEC_E_TRUNC;
+            if (op + len > cap) return MF_DEC_E_DST;
+            for (uint32_t k = 0; k < len; k++) dst[op + k] = src[bp + k];
+            op += len;
+            bitpos = (bp + len) * 8ull;
+            continue;
+        }
+        if (type == 3) return MF_DEC_E_STREAM;
+        uint32_t hlit = 288, hdist = 30;
+        if (type == 1) {
+            int s = 0;
+            for (; s < 144; s++) W.lens[s] = 8;
+            for (; s < 256; s++) W.lens[s] = 9;
+            for (; s < 280; s++) W.lens[s] = 7;
+            for (; s < 288; s++) W.lens[s] = 8;
+            for (s = 0; s < 30; s++) W.lens[288 + s] = 5;
+            mf_canon_build(W.ll, W.lens, 288);
+            mf_canon_build(W.dd, W.lens + 288, 30);
+        } else {
+            int e = mf_read_dynamic_tables(br, W.lens, hlit, hdist);
+            if (e) return e;
+            int r = mf_canon_build(W.ll, W.lens, (int)hlit);
+            if (r < 0 || (r > 0 && (int)hlit - W.ll.count[0] != 1)) return MF_DEC_E_STREAM;
+            r = mf_canon_build(W.dd, W.lens + hlit, (int)hdist);
+            if (r < 0 || (r > 0 && (int)hdist - W.dd.count[0] != 1)) return MF_DEC_E_STREAM;
+        }
+        mf_luts_serial(W.ll, W.lens, (int)hlit, F.lut_ll, MF_LL_LUT_BITS, 9);
+        mf_luts_serial(W.dd, W.lens + hlit, (int)hdist, F.lut_d, MF_D_LUT_BITS, 5);
+        const uint64_t start = br.bitpos(), avail = n * 8ull - start;
+        MfFastReader fr; fr.init(src, start, src + n);
+        for (;;) {
+            fr.fill();
+            const uint32_t e = F.lut_ll[fr.peek(MF_LL_LUT_BITS)];
+            int sym;
+            if (e) { sym = (int)(e & 511u); fr.drop(e >> 9); }
+            else { sym = mf_canon_decode_fast(fr, W.ll.count, W.ll.symbol); if (sym < 0) return fr.used > avail ? MF_DEC_E_TRUNC : MF_DEC_E_STREAM; }
+            if (sym < 256) {
+                if (op >= cap) return fr.used > avail ? MF_DEC_E_TRUNC : MF_DEC_E_DST;
+                dst[op++] = (uint8_t)sym;
+                continue;
+            }
+            if (fr.used > avail) return MF_DEC_E_TRUNC;
+            if (sym == 256) break;
+            sym -= 257;
+            if (sym >= 29) return MF_DEC_E_STREAM;
+            fr.fill();
+            const uint32_t len = mf_lbase(sym) + fr.get(mf_lext(sym));
+            fr.fill();
+            const uint32_t de = F.lut_d[fr.peek(MF_D_LUT_BITS)];
+            int ds;
+            if (de) { ds = (int)(de & 31u); fr.drop(de >> 5); }
+            else { ds = mf_canon_decode_fast(fr, W.dd.count, W.dd.symbol); if (ds < 0) return fr.used > avail ? MF_DEC_E_TRUNC : MF_DEC_E_STREAM; }
+            if (ds >= 30) return MF_DEC_E_STREAM;
+            fr.fill();
+            const uint32_t dist = mf_dbase(ds) + fr.get(mf_dext(ds));
+            if (fr.used > avail) return MF_DEC_E_TRUNC;
+            if (dist > op) return MF_DEC_E_STREAM;
+            if (op + len > cap) return MF_DEC_E_DST;
+            for (uint32_t k = 0; k < len; k++) { dst[op] = dst[op - dist]; op++; }
+        }
+        bitpos = start + fr.used;
+    }
+    *consumed = (bitpos + 7ull) >> 3;
+    *produced = op;
+    return 0;
+}
+
+// foreign streams: one WARP per blob.  A DEFLATE stream without an index is bit-serial, so lane 0 inflates each
+// member (mf_inflate_stream); the member's CRC-32 -- a second pass over its output that cost as much as a sixth
+// of the decode when one lane did it byte by byte -- is computed by the whole warp: 32 contiguous slices,
+// slice-by-4 per lane, GF(2) shifts, xor-reduce.  (One lane per blob, the first version, put 32 unrelated
+// decoders into one warp: they diverge at every symbol and execute one after the other -- 0.7 MB/s per blob.)
+__device__ uint32_t mf_crc_warp(const uint8_t *p, uint64_t n, uint32_t lane) {      // raw (zero-init, no final xor)
+    const uint64_t per = ((n + 31) / 32 + 3) & ~3ull;                           // slice length, a multiple of 4
+    const uint64_t lo = min(n, per * lane), hi = min(n, lo + per);
+    uint32_t crc = 0;
+    uint64_t k = lo;
+    // (the bytes were written by lane 0 moments ago: read them through L2, not through this SM's L1)
+    for (; k < hi && (((uintptr_t)(p + k)) & 3u); k++) crc = g_mf_crc_tab[0][(crc ^ __ldcg(p + k)) & 0xFFu] ^ (crc >> 8);
+    for (; k + 4 <= hi; k += 4) {
+        const uint32_t x = crc ^ __ldcg(reinterpret_cast<const uint32_t *>(p + k));
+        crc = g_mf_crc_tab[3][x & 0xFFu] ^ g_mf_crc_tab[2][(x >> 8) & 0xFFu] ^ g_mf_crc_tab[1][(x >> 16) & 0xFFu] ^ g_mf_crc_tab[0][x >> 24];
+    }
+    for (; k < hi; k++) crc = g_mf_crc_tab[0][(crc ^ __ldcg(p + k)) & 0xFFu] ^ (crc >> 8);
+    crc = mf_gf2_mul(crc, mf_xpow8(n - hi));                                   // shift by the bytes that follow the slice
+    return mf_warp_xor(crc);
+}
+
 __global__ void __launch_bounds__(64)
 mf_gunzip_lane_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, const uint8_t *__restrict__ kind,
                       uint64_t *__restrict__ dst_len, int32_t *__restrict__ status) {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blobs || kind[b] != 1) return;
+    __shared__ MfForeignSmem s_work[2];                                        // one per warp
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (b >= n_blobs || kind[b] != 1) return;                                   // warp-uniform
     const MfDecBlob blob = blobs[b];
-    uint64_t produced = 0;
-    int e = mf_gunzip_stream(blob.src, blob.src_len, blob.dst, blob.dst_cap, &produced, &g_mf_crc_tab[0][0]);
-    status[b] = e;
-    dst_len[b] = e ? 0 : produced;
+    const uint8_t *src = blob.src;
+    const uint64_t n = blob.src_len;
+    uint64_t ip = 0, op = 0;
+    int members = 0, err = 0;
+    while (ip < n && !err) {
+        // lane 0: member header, inflate; the verdict and the extents are broadcast
+        uint64_t used = 0, made = 0;
+        int stop = 0;
+        if (lane == 0) {
+            if (members) { while (ip < n && src[ip] == 0) ip++; }
+            if (ip >= n) stop = 1;
+            else {
+                uint64_t hl = mf_gzip_header_len(src + ip, n - ip, &err);
+                if (hl) {
+                    ip += hl;
+                    err = mf_inflate_stream_dev(src + ip, n - ip, blob.dst + op, blob.dst_cap - op, &used, &made, s_work[threadIdx.x >> 5]);
+                    if (!err) { ip += used; if (ip + 8 > n) err = MF_DEC_E_TRUNC; }
+                }
+            }
+        }
+        stop = __shfl_sync(0xFFFFFFFFu, stop, 0);
+        err = __shfl_sync(0xFFFFFFFFu, err, 0);
+        if (stop || err) break;
+        ip = __shfl_sync(0xFFFFFFFFu, ip, 0);
+        made = __shfl_sync(0xFFFFFFFFu, made, 0);
+        __threadfence();                                                        // lane 0's output bytes, for the other lanes
+        const uint32_t crc = mf_crc_finish(mf_crc_warp(blob.dst + op, made, lane), made);
+        if (crc != mf_le32(src + ip)) err = MF_DEC_E_CRC;
+        else if ((uint32_t)(made & 0xFFFFFFFFull) != mf_le32(src + ip + 4)) err = MF_DEC_E_ISIZE;
+        ip += 8; op += made; members++;
+    }
+    if (!err && !members) err = MF_DEC_E_TRUNC;
+    if (lane == 0) { status[b] = err; dst_len[b] = err ? 0 : op; }
 }

@@ -27,6 +27,10 @@ struct MfBitReader {
         if (skip) { refill(); buf >>= skip; cnt = cnt >= skip ? cnt - skip : 0; }
     }
     MF_HD void refill() {
+        // an aligned 32-bit word at a time where possible (a serial decoder pays every byte load's latency)
+        if (cnt <= 32 && pos + 4 <= n && (((uintptr_t)(p + pos)) & 3u) == 0) {
+            buf |= (uint64_t)(*reinterpret_cast<const uint32_t *>(p + pos)) << cnt; cnt += 32; pos += 4;
+        }
         while (cnt <= 56 && pos < n) { buf |= (uint64_t)p[pos++] << cnt; cnt += 8; }
     }
     MF_HD uint32_t peek(uint32_t k) { if (cnt < k) refill(); return (uint32_t)(buf & ((1ull << k) - 1ull)); }
@@ -136,13 +140,18 @@ MF_HD int mf_read_dynamic_tables(MfBitReader &br, uint8_t *lens, uint32_t &hlit,
 }
 
 // Whole raw-DEFLATE stream, one lane.  dst doubles as the 32 KiB window.
-MF_HD int mf_inflate_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *consumed, uint64_t *produced) {
+// tables of one serial inflater.  The caller decides where they live: on the GPU a per-thread (local-memory) copy is
+// interleaved with the other threads' at a 128-byte stride -- a 1 KiB table is 256 cache lines and every lookup
+// misses L1 -- so the foreign-stream kernel keeps them in shared memory.
+struct MfInflateWork { MfCanon ll, dd; MfCanonLut lut; uint8_t lens[320]; };
+
+MF_HD int mf_inflate_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *consumed, uint64_t *produced, MfInflateWork &work) {
     MfBitReader br; br.init(src, n, 0);
     uint64_t op = 0;
     uint32_t last = 0;
-    MfCanon ll, dd;
-    MfCanonLut lut;
-    uint8_t lens[320];
+    MfCanon &ll = work.ll, &dd = work.dd;
+    MfCanonLut &lut = work.lut;
+    uint8_t *lens = work.lens;
     while (!last) {
         last = br.get(1);
         uint32_t type = br.get(2);
@@ -257,7 +266,8 @@ MF_HD int mf_gunzip_stream(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_
         if (!hl) return err;
         ip += hl;
         uint64_t used = 0, made = 0;
-        int e = mf_inflate_stream(src + ip, n - ip, dst + op, cap - op, &used, &made);
+        MfInflateWork work;
+        int e = mf_inflate_stream(src + ip, n - ip, dst + op, cap - op, &used, &made, work);
         if (e) return e;
         ip += used;
         if (ip + 8 > n) return MF_DEC_E_TRUNC;

@@ -530,7 +530,7 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     mf_verify_kernel<<<(unsigned)((max_members * 32 + 127) / 128), 128, 0, s>>>(
         reinterpret_cast<const MfDecMember *>(dw + o_members), cnt, reinterpret_cast<const uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
-    mf_gunzip_lane_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len),
+    mf_gunzip_lane_kernel<<<(unsigned)((n + 1) / 2), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len),
                                                                   reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
     D.launches += 4;
