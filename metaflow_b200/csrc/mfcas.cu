@@ -263,7 +263,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
         for (uint64_t i = 0; i < n; i++) { n_members += mf_n_members(src_len[i]); n_chunks += mf_n_chunks(src_len[i]); }
-    const uint64_t max_groups = n_chunks / MF_ENC_GROUP + n_members;      // encoder work units: <= 16 chunks of one member
+    const uint64_t max_groups = n_chunks / MF_ENC_GROUP + n_members;      // encoder work units: <= MF_ENC_GROUP chunks of one member
     if (n_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
     Carver hc;
     const size_t o_hash = hc.take(sizeof(MfHashDesc) * n);
