@@ -417,3 +417,31 @@ def test_c_abi_contract_edges(gpu_codec):
     assert lib.mfcas_unpack_batch(ctx, 0, None, None, None, None, None, None) == capi.OK
     assert lib.mfcas_pack_batch(ctx, 1, None, None, None, None, None, None, None) == capi.E_ARG
     assert lib.mfcas_pack_batch(None, 1, src, slen, dst, dcap, dlen, sha, st) == capi.E_ARG
+
+
+def test_client_filecache_batched_fetch_on_gpu(gpu_codec, tmp_path):
+    """the client file cache in front of the GPU datastore -- the artifacts of a whole step are
+    fetched with ONE batched unpack, land in the on-disk cache, and come from there the second time."""
+    from metaflow_b200 import FlowDataStore, LocalStorage
+    from metaflow_b200.client import FileCache
+    rng = np.random.default_rng(51)
+    fds = FlowDataStore("ClientFlow", storage_impl=LocalStorage, ds_root=str(tmp_path / "ds"), codec=gpu_codec)
+    arrays = [rng.standard_normal(60000 + 1000 * t, dtype=np.float32) for t in range(12)]
+    for t, a in enumerate(arrays):
+        w = fds.get_task_datastore("3", "train", str(t), attempt=0, mode="w")
+        w.init_task()
+        w.save_artifacts(iter([("weights", a), ("tag", "t%d" % t)]))
+        w.done()
+    fc = FileCache(cache_dir=str(tmp_path / "cache"), max_size=1000, codec=gpu_codec)
+    tasks = [("3", "train", str(t), None) for t in range(12)]
+    l0 = gpu_codec.counters()["kernel_launches"]
+    out = fc.get_artifacts_for_tasks("local", str(tmp_path / "ds"), "ClientFlow", tasks, ["weights", "tag"])
+    l1 = gpu_codec.counters()["kernel_launches"]
+    assert l1 - l0 == 4                                             # parse + inflate + verify + foreign: one batch for 24 blobs
+    for t, a in enumerate(arrays):
+        got = out[("3", "train", str(t))]
+        assert np.array_equal(got["weights"], a) and got["tag"] == "t%d" % t
+    again = fc.get_artifacts_for_tasks("local", str(tmp_path / "ds"), "ClientFlow", tasks, ["weights"])
+    assert gpu_codec.counters()["kernel_launches"] == l1             # all from the cache files
+    assert np.array_equal(again[("3", "train", "7")]["weights"], arrays[7])
+    assert np.array_equal(fc.get_artifact("local", str(tmp_path / "ds"), None, "ClientFlow", "3", "train", "5", "weights"), arrays[5])
