@@ -473,7 +473,7 @@ __device__ __forceinline__ uint32_t mf_lane_emit_dev(const uint8_t *seg, uint32_
 #define MF_ENC_THREADS 512
 #define MF_ENC_WARPS 16
 #define MF_HASH_BITS 10
-#define MF_ENC_GROUP 32u         // consecutive chunks of a member handed to one CTA: codes may be carried inside a group
+#define MF_ENC_GROUP 64u         // consecutive chunks of a member handed to one CTA: codes may be carried inside a group
 #define MF_HDR_CACHE_WORDS 192u
 #define MF_REGION_B 34816u      // hash tables in pass 2 (32 KiB), packed output words afterwards
 

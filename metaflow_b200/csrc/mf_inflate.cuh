@@ -137,7 +137,7 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
 
 // ------------------------------------------------------------------ chunk decoder
 #define MF_DEC_WARPS 8
-#define MF_DEC_GROUP 32u      // consecutive chunks per warp (header/LUT reuse)
+#define MF_DEC_GROUP 64u      // consecutive chunks per warp (header/LUT reuse)
 #define MF_LL_LUT_BITS 10
 #define MF_D_LUT_BITS 8
 

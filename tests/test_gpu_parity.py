@@ -120,7 +120,7 @@ def test_distributions_and_ratio(gpu_codec):
 
 
 def test_codes_carried_inside_a_group(gpu_codec):
-    """The encoder keeps the Huffman codes of the previous chunk of a 32-chunk group while they stay within 1/128 of
+    """The encoder keeps the Huffman codes of the previous chunk of a 64-chunk group while they stay within 1/128 of
     fresh ones.  Mix chunk kinds inside groups (stationary noise, sudden switches, symbols the kept code does not
     cover, incompressible and empty-ish chunks): every stream must stay valid for zlib and for our decoder, packed
     bytes must not depend on the batch around a blob, and the kept codes must not cost ratio on stationary data."""
