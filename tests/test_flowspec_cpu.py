@@ -183,3 +183,44 @@ def test_same_artifact_keys_as_the_real_reference(tmp_path):
         theirs = ref_keys[mine["seed"]]
         for name in ("arr", "seed", "common", "seeds"):
             assert mine[name] == theirs[name], name
+
+
+def test_wide_foreach_is_still_one_batch_per_step(tmp_path):
+    """The reference's `wide_foreach` core test shape (1200 splits): every sibling's artifacts go to the codec as one
+    batch per step, the join sees all inputs in order, and identical artifacts of the siblings are stored once."""
+    from metaflow_b200.flowspec import FlowSpec, step
+
+    class WideFlow(FlowSpec):
+        @step
+        def start(self):
+            self.items = list(range(1200))
+            self.next(self.each, foreach="items")
+
+        @step
+        def each(self):
+            self.sq = self.input * self.input
+            self.same = "identical in every split"
+            self.next(self.join)
+
+        @step
+        def join(self, inputs):
+            self.n = len(inputs)
+            self.total = sum(inp.sq for inp in inputs)
+            self.first_last = (inputs[0].sq, inputs[-1].sq)
+            self.next(self.end)
+
+        @step
+        def end(self):
+            pass
+
+    codec = OracleCodec()
+    run = FlowRunner(WideFlow, ds_root=str(tmp_path / "ds"), codec=codec).run()
+    assert codec.calls["pack"] == 4                                  # start, each x1200, join, end
+    j = run.task_datastores("join")[0]
+    assert j["n"] == 1200 and j["total"] == sum(i * i for i in range(1200)) and j["first_last"] == (0, 1199 * 1199)
+    each = run.task_datastores("each")
+    assert len(each) == 1200 and each[777]["sq"] == 777 * 777
+    keys = {ds._objects["same"] for ds in each}
+    assert len(keys) == 1                                            # content-addressed: one blob for 1200 identical artifacts
+    blob_files = [f for _, _, fs in os.walk(tmp_path / "ds" / "WideFlow" / "data") for f in fs if not f.endswith("_meta")]
+    assert len(blob_files) == len(set(blob_files))
