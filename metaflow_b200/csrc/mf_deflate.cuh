@@ -6,14 +6,18 @@
 // :259-285, :302-314, :350-360).  Output is a different (chunked, indexed) but equally valid
 // RFC 1952 byte stream: parity is defined on the decoded bytes.
 //
-// One CTA (16 warps) owns one 32 KiB chunk staged in shared memory:
+// Persistent CTAs (16 warps) take groups of MF_ENC_GROUP consecutive chunks of a member by ticket; per 32 KiB chunk,
+// staged in shared memory:
 //   pass 0  coalesced 16-byte loads HBM -> smem
-//   pass 1  CRC-32 of the chunk (64-byte piece per lane, slice-by-4 tables in smem, GF(2) combine)
 //   pass 2  LZ77: each warp walks its 1 KiB segments 32 positions at a time (hash probe + in-window
-//           probes via warp shuffles, cooperative match extension, ballot-ordered greedy parse)
+//           probes via warp shuffles, cooperative match extension, ballot-ordered greedy parse); in stretches
+//           without matches only every 4th / 8th / 16th window is probed
+//   pass 3a price the chunk with the previous chunk's code lengths against its own entropy bound: within 1/128
+//           the codes and the block header are kept (then pass 3 is only CRC-32 + a header copy)
 //   pass 3  prefix codes by Kraft-slack refinement, warp-synchronous in registers (warp 0 literal/length,
-//           warp 1 distance), then the dynamic-block header with position-parallel run-length tokens
-//   pass 4  per-lane bit counting, warp-shuffle prefix scans -> every token's bit offset
+//           warp 1 distance), then the dynamic-block header with position-parallel run-length tokens;
+//           CRC-32 of the chunk meanwhile (64-byte piece per lane, slice-by-4 tables in smem, GF(2) combine)
+//   pass 4  per-lane bit counting out of registers, warp-shuffle prefix scans -> every token's bit offset
 //   pass 5  bit packing into smem, then coalesced 16-byte stores smem -> HBM slot
 // HBM traffic per chunk: raw bytes read once, packed bytes written once (+ the gather copy).
 #pragma once

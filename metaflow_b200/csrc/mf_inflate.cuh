@@ -5,8 +5,9 @@
 //
 //   mf_parse_kernel          one warp per blob: walk the RFC 1952 members; 'MF'-indexed members are
 //                            expanded into chunk descriptors, anything else is flagged "foreign"
-//   mf_inflate_chunk_kernel  one warp per 32 KiB chunk, one LANE per 1 KiB segment: lane 0 parses the
-//                            block header, the warp builds lookup tables with match.any ranks, then
+//   mf_inflate_chunk_kernel  a warp takes MF_DEC_GROUP consecutive 32 KiB chunks, one LANE per 1 KiB segment:
+//                            lane 0 parses a block header and the warp builds lookup tables with match.any
+//                            ranks (skipped while the header repeats the previous chunk's), then
 //                            32 lanes Huffman-decode 32 segments concurrently (the index gives every
 //                            segment's bit offset; LZ77 matches never leave a segment); each lane writes
 //                            its segment to HBM 16 bytes at a time from registers and folds the CRC-32
