@@ -11,13 +11,13 @@ class ImmutableBlobCache(BlobCache):
     """Serves only what was preloaded; never stores (datastore_set.py:76-85)."""
 
     def __init__(self, preloaded):
-        self._preloaded = preloaded
+        self._blobs = dict(preloaded)
 
     def load_key(self, key):
-        return self._preloaded.get(key)
+        return self._blobs.get(key)
 
     def store_key(self, key, blob):
-        pass
+        return None
 
 
 class TaskDataStoreSet(object):
@@ -27,25 +27,21 @@ class TaskDataStoreSet(object):
             run_id, steps=steps, pathspecs=pathspecs, allow_not_done=allow_not_done, join_type=join_type,
             orig_flow_datastore=orig_flow_datastore, spin_artifacts=spin_artifacts)
         if prefetch_data_artifacts:
-            wanted = set()
-            for ds in self.task_datastores:
-                wanted.update(ds.keys_for_artifacts(prefetch_data_artifacts))
-            wanted.discard(None)
-            preloaded = dict(flow_datastore.ca_store.load_blobs(wanted))   # ONE batched GPU unpack
-            flow_datastore.ca_store.set_blob_cache(ImmutableBlobCache(preloaded))
-        self.pathspec_index_cache = {}
-        self.pathspec_cache = {}
-        if not allow_not_done:
-            for ds in self.task_datastores:
-                self.pathspec_index_cache[ds.pathspec_index] = ds
-                self.pathspec_cache[ds.pathspec] = ds
+            self._prefetch(flow_datastore.ca_store, prefetch_data_artifacts)
+        done = [] if allow_not_done else self.task_datastores       # unfinished tasks have no stable pathspec index
+        self.pathspec_index_cache = {ds.pathspec_index: ds for ds in done}
+        self.pathspec_cache = {ds.pathspec: ds for ds in done}
+
+    def _prefetch(self, ca_store, names):
+        """All distinct keys behind `names` in all tasks -> ONE batched GPU unpack -> a read-only blob cache."""
+        keys = {k for ds in self.task_datastores for k in ds.keys_for_artifacts(names) if k is not None}
+        ca_store.set_blob_cache(ImmutableBlobCache(ca_store.load_blobs(keys)))
 
     def get_with_pathspec(self, pathspec):
-        return self.pathspec_cache.get(pathspec, None)
+        return self.pathspec_cache.get(pathspec)
 
     def get_with_pathspec_index(self, pathspec_index):
-        return self.pathspec_index_cache.get(pathspec_index, None)
+        return self.pathspec_index_cache.get(pathspec_index)
 
     def __iter__(self):
-        for ds in self.task_datastores:
-            yield ds
+        return iter(self.task_datastores)
