@@ -37,13 +37,75 @@ class FileCacheException(MetaflowException):
     headline = "File cache error"
 
 
+def _silent_unlink(path):
+    try:
+        os.unlink(path)
+    except OSError:
+        pass
+
+
+class _CacheIndex(object):
+    """What is in the cache directory, oldest first, and how much it weighs.  Built lazily (walking the directory
+    can be expensive), appended to on every write, trimmed to the size budget oldest-first -- but never a file
+    younger than NEW_FILE_QUARANTINE seconds, which another process may just be about to read."""
+
+    SUFFIXES = (".cached", ".blob")
+
+    def __init__(self, root, budget_bytes):
+        self.root, self.budget, self.total, self.entries = root, budget_bytes, 0, None
+
+    def _scan(self):
+        found = []
+        if os.path.isdir(self.root):
+            for ds_id in os.listdir(self.root):
+                for sub, _dirs, files in _two_levels(os.path.join(self.root, ds_id)):
+                    for name in files:
+                        if name.endswith(self.SUFFIXES):
+                            path = os.path.join(sub, name)
+                            try:
+                                found.append((os.path.getctime(path), os.path.getsize(path), path))
+                            except OSError:
+                                pass
+        found.sort()
+        self.entries, self.total = found, sum(size for _, size, _ in found)
+
+    def added(self, path):
+        if self.entries is None:
+            self._scan()
+            if any(p == path for _, _, p in self.entries):
+                return self.trim()
+        size = os.path.getsize(path)
+        self.entries.append((int(time.time()), size, path))
+        self.total += size
+        self.trim()
+
+    def trim(self):
+        now = time.time()
+        while self.entries and self.total > self.budget and now - self.entries[0][0] >= NEW_FILE_QUARANTINE:
+            _, size, path = self.entries.pop(0)
+            self.total -= size
+            try:
+                os.remove(path)
+            except OSError:
+                pass                          # another client removed it already
+
+
+def _two_levels(ds_dir):
+    """<cache>/<ds id>/<two hex chars>/<files>: yields (subdir, [], files) for every second-level directory."""
+    if not os.path.isdir(ds_dir):
+        return
+    for sub in os.listdir(ds_dir):
+        subdir = os.path.join(ds_dir, sub)
+        if os.path.isdir(subdir):
+            yield subdir, [], os.listdir(subdir)
+
+
 class FileCache(object):
     def __init__(self, cache_dir=None, max_size=None, codec=None):
         self._cache_dir = cache_dir if cache_dir is not None else metaflow_config.CLIENT_CACHE_PATH
         self._max_size = int(max_size if max_size is not None else metaflow_config.CLIENT_CACHE_MAX_SIZE)
         self._codec = codec                  # GpuCodec to hand to the datastores (None: the process-wide one)
-        self._total = 0
-        self._objects = None                 # [(ctime, size, path)] oldest first; indexed lazily
+        self._index = _CacheIndex(self._cache_dir, self._max_size * 1024 ** 2)
         self._blob_caches = {}               # flow_ds_id -> (FileBlobCache, TaskMetadataCache)
         self._store_caches = OrderedDict()   # flow_ds_id -> FlowDataStore, least recently used first
 
@@ -96,29 +158,25 @@ class FileCache(object):
 
     # ---------------------------------------------------------------- cache files
     def create_file(self, path, value):
-        if self._objects is None:
-            self._index_objects()            # lazily: walking the cache can be expensive
         dirname = os.path.dirname(path)
         try:
             os.makedirs(dirname, exist_ok=True)
         except OSError:
             raise FileCacheException("Could not create directory: %s" % dirname)
-        tmpfile = NamedTemporaryFile(dir=dirname, prefix="dlobj", delete=False)
-        try:
-            tmpfile.write(value)
-            tmpfile.flush()
-            tmpfile.close()
-            os.rename(tmpfile.name, path)
-        except BaseException:
+        with NamedTemporaryFile(dir=dirname, prefix="dlobj", delete=False) as tmp:
+            tmp_name = tmp.name
             try:
-                os.unlink(tmpfile.name)
-            except OSError:
-                pass
+                tmp.write(value)
+            except BaseException:
+                tmp.close()
+                _silent_unlink(tmp_name)
+                raise
+        try:
+            os.rename(tmp_name, path)          # readers see the whole file or none of it
+        except BaseException:
+            _silent_unlink(tmp_name)
             raise
-        size = os.path.getsize(path)
-        self._total += size
-        self._objects.append((int(time.time()), size, path))
-        self._garbage_collect()
+        self._index.added(path)
 
     def read_file(self, path):
         if os.path.exists(path):
@@ -128,39 +186,6 @@ class FileCache(object):
             except IOError:
                 pass                          # garbage collected by another process meanwhile
         return None
-
-    def _index_objects(self):
-        objects = []
-        if os.path.exists(self._cache_dir):
-            for ds_id in os.listdir(self._cache_dir):
-                root = os.path.join(self._cache_dir, ds_id)
-                if not os.path.isdir(root):
-                    continue
-                for subdir in os.listdir(root):
-                    sub = os.path.join(root, subdir)
-                    if not os.path.isdir(sub):
-                        continue
-                    for obj in os.listdir(sub):
-                        if os.path.splitext(obj)[1] in (".cached", ".blob"):
-                            path = os.path.join(sub, obj)
-                            try:
-                                objects.append((os.path.getctime(path), os.path.getsize(path), path))
-                            except OSError:
-                                pass
-        self._total = sum(size for _, size, _ in objects)
-        self._objects = sorted(objects)
-
-    def _garbage_collect(self):
-        now = time.time()
-        while self._objects and self._total > self._max_size * 1024 ** 2:
-            if now - self._objects[0][0] < NEW_FILE_QUARANTINE:
-                break
-            _, size, path = self._objects.pop(0)
-            self._total -= size
-            try:
-                os.remove(path)
-            except OSError:
-                pass                          # another client removed it already
 
     # ---------------------------------------------------------------- ids
     @staticmethod
