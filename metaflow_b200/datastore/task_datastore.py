@@ -76,6 +76,11 @@ def _unpickle_pool():
     return _pool
 
 
+def _read_only(attr):
+    """A property that exposes a private attribute."""
+    return property(lambda self: getattr(self, attr))
+
+
 class TaskDataStore(object):
     METADATA_ATTEMPT_SUFFIX = "attempt.json"
     METADATA_DONE_SUFFIX = "DONE.lock"
@@ -146,29 +151,19 @@ class TaskDataStore(object):
         return latest
 
     # -- identity --------------------------------------------------------------------------
+    run_id = _read_only("_run_id")
+    step_name = _read_only("_step_name")
+    task_id = _read_only("_task_id")
+    attempt = _read_only("_attempt")
+
     @property
     def pathspec(self):
-        return "/".join([self.run_id, self.step_name, self.task_id])
-
-    @property
-    def run_id(self):
-        return self._run_id
-
-    @property
-    def step_name(self):
-        return self._step_name
-
-    @property
-    def task_id(self):
-        return self._task_id
-
-    @property
-    def attempt(self):
-        return self._attempt
+        return "%s/%s/%s" % (self._run_id, self._step_name, self._task_id)
 
     @property
     def ds_metadata(self):
-        return {"objects": self._objects.copy(), "info": self._info.copy()}
+        """What a MetadataCache stores for this task: copies of the name->key and name->info maps."""
+        return {"objects": dict(self._objects), "info": dict(self._info)}
 
     @property
     def pathspec_index(self):
