@@ -7,4 +7,14 @@ from .exception import (DataException, GpuCasUnavailable, MetaflowException, Met
 from .datastore import (ContentAddressedStore, FlowDataStore, Inputs, TaskDataStore, TaskDataStoreSet)
 from .plugins.datastores.local_storage import LocalStorage
 
+from .flowspec import FlowRunner, FlowSpec, step
+
 __version__ = "0.1.0"
+
+
+def __getattr__(name):            # `metaflow_b200.FileCache` without importing the client package up front
+    if name in ("FileCache", "FileBlobCache", "TaskMetadataCache"):
+        from . import client
+
+        return getattr(client, name)
+    raise AttributeError("module 'metaflow_b200' has no attribute '%s'" % name)

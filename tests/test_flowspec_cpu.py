@@ -224,3 +224,13 @@ def test_wide_foreach_is_still_one_batch_per_step(tmp_path):
     assert len(keys) == 1                                            # content-addressed: one blob for 1200 identical artifacts
     blob_files = [f for _, _, fs in os.walk(tmp_path / "ds" / "WideFlow" / "data") for f in fs if not f.endswith("_meta")]
     assert len(blob_files) == len(set(blob_files))
+
+
+def test_top_level_api_surface():
+    """`from metaflow_b200 import FlowSpec, step` -- the names a flow file imports from `metaflow`."""
+    import metaflow_b200 as mf
+    for name in ("FlowSpec", "step", "FlowRunner", "FlowDataStore", "TaskDataStore", "ContentAddressedStore", "LocalStorage",
+                 "TaskDataStoreSet", "Inputs", "DataException", "FileCache"):
+        assert getattr(mf, name) is not None, name
+    with pytest.raises(AttributeError):
+        mf.no_such_name
