@@ -37,3 +37,414 @@ def pack_sharded(codec, blobs, rank=0, world=1, all_gather=None):
         return keys, packed
     gathered = all_gather(keys)
     return merge_shard_results(len(blobs), gathered), packed
+
+
+# ------------------------------------------------------------------------------------------------------
+# The multi-process batcher: ONE process per box owns the GPU context(s); task processes -- the children
+# multicore_utils.parallel_map forks, or stock one-process-per-task runs (metaflow/runtime.py:1517-1577,
+# 2287-2350) pointed at a running daemon -- hand their blobs over through files in shared memory
+# (/dev/shm) and small messages on a Unix socket.  Requests that arrive while a GPU batch is running are
+# merged into the next one, so N concurrently saving tasks become one wide batch (a SHA-1 lane does
+# ~150 MB/s; width is what makes the GPU path fast), sharded round-robin over the GPUs by libmfcas.
+#
+#   server:  CodecServer(codec).start()        or   python -m metaflow_b200.batcher serve [--socket PATH]
+#   client:  METAFLOW_GPU_CAS_SERVER=<socket path>  ->  codec.default_codec() returns a RemoteCodec
+import mmap
+import os
+import pickle
+import queue
+import socket
+import struct
+import tempfile
+import threading
+
+SERVER_ENV = "METAFLOW_GPU_CAS_SERVER"
+_SHM_DIR = "/dev/shm" if os.path.isdir("/dev/shm") else None
+
+
+def _send_msg(sock, obj):
+    data = pickle.dumps(obj, protocol=4)
+    sock.sendall(struct.pack("<Q", len(data)) + data)
+
+
+def _recv_exact(sock, n):
+    buf = bytearray()
+    while len(buf) < n:
+        chunk = sock.recv(min(n - len(buf), 1 << 20))
+        if not chunk:
+            raise EOFError("peer closed the batcher socket")
+        buf += chunk
+    return bytes(buf)
+
+
+def _recv_msg(sock):
+    (n,) = struct.unpack("<Q", _recv_exact(sock, 8))
+    return pickle.loads(_recv_exact(sock, n))
+
+
+def _layout(lens):
+    """Byte offsets of blobs laid out back to back at 64-byte aligned positions -> (offsets, total)."""
+    offs, cur = [], 0
+    for ln in lens:
+        offs.append(cur)
+        cur += (ln + 63) // 64 * 64
+    return offs, cur
+
+
+class _Segment(object):
+    """A file in shared memory holding a list of byte strings; the path is what crosses the socket."""
+
+    def __init__(self, path, size, create):
+        self.path, self.size = path, size
+        flags = os.O_RDWR | (os.O_CREAT | os.O_EXCL if create else 0)
+        fd = os.open(path, flags, 0o600)
+        try:
+            if create:
+                os.ftruncate(fd, max(size, 1))
+            self.map = mmap.mmap(fd, max(size, 1))
+        finally:
+            os.close(fd)
+        self.view = memoryview(self.map)
+
+    @classmethod
+    def create(cls, size, dir=None):
+        fd, path = tempfile.mkstemp(prefix="mfcas_seg_", dir=dir or _SHM_DIR)
+        os.close(fd)
+        os.unlink(path)
+        return cls(path, size, True)
+
+    def unlink(self):
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+    def close(self):
+        try:
+            self.view.release()
+            self.map.close()
+        except (BufferError, ValueError):
+            pass                       # views handed to the caller are still alive: the mapping goes with them
+
+
+class _Request(object):
+    __slots__ = ("op", "items", "reply", "done", "result", "error")
+
+    def __init__(self, op, items):
+        self.op, self.items = op, items
+        self.done = threading.Event()
+        self.result = self.error = None
+
+
+class CodecServer(object):
+    """Owns `codec` (a GpuCodec) and serves pack / hash / unpack requests of other processes, merging
+    concurrent requests of the same kind into one codec call."""
+
+    def __init__(self, codec, socket_path=None, linger=0.002, max_batch_bytes=4 << 30):
+        self.codec = codec
+        self.linger = linger
+        self.max_batch_bytes = max_batch_bytes
+        if socket_path is None:
+            d = tempfile.mkdtemp(prefix="mfcas_srv_")
+            socket_path = os.path.join(d, "sock")
+        self.socket_path = socket_path
+        self._sock = None
+        self._q = queue.Queue()
+        self._stop = threading.Event()
+        self._threads = []
+        self.batches = {"pack": 0, "hash": 0, "unpack": 0}       # codec calls issued (tests read this)
+        self.requests = 0
+
+    # -- lifecycle
+    def start(self):
+        if os.path.exists(self.socket_path):
+            os.unlink(self.socket_path)
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.bind(self.socket_path)
+        s.listen(256)
+        s.settimeout(0.2)
+        self._sock = s
+        for target in (self._accept_loop, self._batch_loop):
+            t = threading.Thread(target=target, daemon=True, name="mfcas-" + target.__name__)
+            t.start()
+            self._threads.append(t)
+        return self
+
+    def stop(self):
+        self._stop.set()
+        self._q.put(None)
+        for t in self._threads:
+            t.join(timeout=5)
+        if self._sock is not None:
+            self._sock.close()
+        try:
+            os.unlink(self.socket_path)
+        except OSError:
+            pass
+
+    def __enter__(self):
+        return self.start()
+
+    def __exit__(self, *exc):
+        self.stop()
+
+    # -- connections: one thread per client, requests answered in order
+    def _accept_loop(self):
+        while not self._stop.is_set():
+            try:
+                conn, _ = self._sock.accept()
+            except socket.timeout:
+                continue
+            except OSError:
+                return
+            threading.Thread(target=self._serve, args=(conn,), daemon=True, name="mfcas-conn").start()
+
+    def _serve(self, conn):
+        with conn:
+            while not self._stop.is_set():
+                try:
+                    msg = _recv_msg(conn)
+                except (EOFError, OSError):
+                    return
+                seg = None
+                try:
+                    op = msg["op"]
+                    if op == "ping":
+                        _send_msg(conn, {"ok": True, "pid": os.getpid()})
+                        continue
+                    items = []
+                    if msg.get("segment"):
+                        seg = _Segment(msg["segment"], msg["size"], False)
+                        offs, _ = _layout(msg["lens"])
+                        items = [seg.view[o:o + ln] for o, ln in zip(offs, msg["lens"])]
+                    # unpack requests may name files instead: the server reads them straight into pinned memory
+                    for k, path in sorted(msg.get("files", {}).items()):
+                        items.insert(k, self._file_source(path))
+                    req = _Request(op, items)
+                    self._q.put(req)
+                    req.done.wait()
+                    if req.error is not None:
+                        _send_msg(conn, {"ok": False, "error": req.error})
+                    else:
+                        _send_msg(conn, req.result)
+                except (OSError, KeyError, ValueError) as e:
+                    try:
+                        _send_msg(conn, {"ok": False, "error": "%s: %s" % (type(e).__name__, e)})
+                    except OSError:
+                        return
+                finally:
+                    if seg is not None:
+                        items = None
+                        seg.close()
+
+    def _file_source(self, path):
+        if getattr(self.codec, "accepts_file_sources", False):
+            from .codec import FileSource
+
+            return FileSource(path, os.path.getsize(path))
+        with open(path, "rb") as f:
+            return f.read()
+
+    # -- the batcher proper
+    def _batch_loop(self):
+        while True:
+            first = self._q.get()
+            if first is None:
+                return
+            batch, size = [first], sum(len(b) for b in first.items)
+            deadline = self.linger
+            held = []
+            while size < self.max_batch_bytes:
+                try:
+                    nxt = self._q.get(timeout=deadline)
+                except queue.Empty:
+                    break
+                if nxt is None:
+                    self._q.put(None)
+                    break
+                if nxt.op != first.op:
+                    held.append(nxt)
+                    continue
+                batch.append(nxt)
+                size += sum(len(b) for b in nxt.items)
+                deadline = 0.0005
+            for h in held:
+                self._q.put(h)
+            self._run(first.op, batch)
+
+    def _run(self, op, batch):
+        self.requests += len(batch)
+        flat = [b for r in batch for b in r.items]
+        try:
+            if op == "hash":
+                keys = self.codec.hash_batch(flat) if flat else []
+                self.batches["hash"] += 1
+                pos = 0
+                for r in batch:
+                    r.result = {"ok": True, "keys": keys[pos:pos + len(r.items)]}
+                    pos += len(r.items)
+            elif op == "pack":
+                keys, packed = self.codec.pack_batch(flat) if flat else ([], [])
+                self.batches["pack"] += 1
+                pos = 0
+                for r in batch:
+                    mine = packed[pos:pos + len(r.items)]
+                    r.result = dict(self._export([getattr(p, "views", [p]) for p in mine]), ok=True, keys=keys[pos:pos + len(r.items)])
+                    pos += len(r.items)
+            elif op == "unpack":
+                out = self.codec.unpack_batch(flat, as_bytes=False) if flat else []
+                self.batches["unpack"] += 1
+                pos = 0
+                for r in batch:
+                    mine = out[pos:pos + len(r.items)]
+                    errors = {i: (getattr(o, "code", -1), str(o)) for i, o in enumerate(mine) if isinstance(o, Exception)}
+                    r.result = dict(self._export([[o] if not isinstance(o, Exception) else [] for o in mine]), ok=True, errors=errors)
+                    pos += len(r.items)
+            else:
+                raise ValueError("unknown op %r" % (op,))
+        except Exception as e:  # noqa: BLE001 -- a failed batch is reported to every client that was part of it
+            for r in batch:
+                r.result, r.error = None, "%s: %s" % (type(e).__name__, e)
+        for r in batch:
+            r.done.set()
+
+    @staticmethod
+    def _export(pieces_per_blob):
+        """[[bytes-like piece, ...] per blob] -> a result segment: every blob's pieces joined, back to back."""
+        lens = [sum(len(p) for p in pieces) for pieces in pieces_per_blob]
+        offs, total = _layout(lens)
+        seg = _Segment.create(total)
+        for o, pieces in zip(offs, pieces_per_blob):
+            cur = o
+            for p in pieces:
+                seg.view[cur:cur + len(p)] = p
+                cur += len(p)
+        seg.close()
+        return {"segment": seg.path, "size": total, "lens": lens}
+
+
+class RemoteCodec(object):
+    """The GpuCodec interface (hash_batch / pack_batch / unpack_batch) served by a CodecServer in another
+    process.  Results are views over a shared-memory mapping that lives as long as they do."""
+
+    accepts_file_sources = True
+
+    def __init__(self, socket_path=None):
+        from .exception import GpuCasUnavailable
+
+        self.socket_path = socket_path or os.environ.get(SERVER_ENV)
+        if not self.socket_path:
+            raise GpuCasUnavailable("no batcher address: set %s" % SERVER_ENV)
+        try:
+            self._sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            self._sock.connect(self.socket_path)
+        except OSError as e:
+            raise GpuCasUnavailable("cannot reach the GPU batcher at %s: %s" % (self.socket_path, e))
+        self._lock = threading.Lock()
+
+    def close(self):
+        try:
+            self._sock.close()
+        except OSError:
+            pass
+
+    def ping(self):
+        with self._lock:
+            _send_msg(self._sock, {"op": "ping"})
+            return _recv_msg(self._sock)
+
+    def _call(self, op, blobs):
+        from .codec import FileSource
+        from .exception import DataException
+        from .serializer import Segments
+
+        files = {i: b.path for i, b in enumerate(blobs) if isinstance(b, FileSource)}
+        mem = [b for b in blobs if not isinstance(b, FileSource)]
+        lens = [len(b) for b in mem]
+        offs, total = _layout(lens)
+        seg = None
+        msg = {"op": op, "files": files}
+        try:
+            if mem:
+                seg = _Segment.create(total)
+                import numpy as np
+
+                arr = np.frombuffer(seg.view, dtype=np.uint8)
+                for o, ln, b in zip(offs, lens, mem):
+                    if not ln:
+                        continue
+                    if isinstance(b, Segments):
+                        b.copy_into(arr, o)
+                    else:
+                        seg.view[o:o + ln] = b
+                del arr
+                msg.update(segment=seg.path, size=total, lens=lens)
+            with self._lock:
+                _send_msg(self._sock, msg)
+                rep = _recv_msg(self._sock)
+        finally:
+            if seg is not None:
+                seg.unlink()
+                seg.close()
+        if not rep.get("ok"):
+            raise DataException("GPU batcher call failed: %s" % rep.get("error"))
+        return rep
+
+    @staticmethod
+    def _import(rep):
+        out_seg = _Segment(rep["segment"], rep["size"], False)
+        out_seg.unlink()                                   # the mapping keeps the pages until the views die
+        offs, _ = _layout(rep["lens"])
+        return [out_seg.view[o:o + ln] for o, ln in zip(offs, rep["lens"])]
+
+    def hash_batch(self, blobs):
+        if not blobs:
+            return []
+        return self._call("hash", list(blobs))["keys"]
+
+    def pack_batch(self, blobs):
+        from .codec import Packed
+
+        if not blobs:
+            return [], []
+        rep = self._call("pack", list(blobs))
+        return rep["keys"], [Packed([v]) for v in self._import(rep)]
+
+    def unpack_batch(self, packed_blobs, as_bytes=True):
+        from .codec import UnpackError
+
+        if not packed_blobs:
+            return []
+        rep = self._call("unpack", list(packed_blobs))
+        views = self._import(rep)
+        out = []
+        for i, v in enumerate(views):
+            if i in rep["errors"]:
+                out.append(UnpackError(rep["errors"][i][0]))
+            else:
+                out.append(bytes(v) if as_bytes else v)
+        return out
+
+
+def serve_forever(socket_path, devices=None):
+    from .codec import GpuCodec
+
+    server = CodecServer(GpuCodec(devices=devices), socket_path=socket_path).start()
+    print("mfcas batcher serving on %s (export %s=%s)" % (server.socket_path, SERVER_ENV, server.socket_path), flush=True)
+    try:
+        threading.Event().wait()
+    except KeyboardInterrupt:
+        pass
+    finally:
+        server.stop()
+
+
+if __name__ == "__main__":
+    import argparse
+
+    ap = argparse.ArgumentParser(description="GPU artifact batcher daemon")
+    ap.add_argument("cmd", choices=["serve"])
+    ap.add_argument("--socket", default=os.path.join(tempfile.gettempdir(), "mfcas_batcher_%d.sock" % os.getuid()))
+    ap.add_argument("--devices", default="")
+    a = ap.parse_args()
+    serve_forever(a.socket, [int(x) for x in a.devices.split(",") if x] or None)

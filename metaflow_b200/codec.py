@@ -6,6 +6,9 @@ _unpack_v1) with mfcas_pack_batch / mfcas_hash_batch / mfcas_unpack_batch on the
 Blobs are packed into page-locked arenas so every wave moves with one cudaMemcpyAsync each way.
 """
 import ctypes
+import os
+import struct
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -53,6 +56,45 @@ class _PinnedArena(object):
             self._lib.mfcas_free_pinned(self._ptr)
             self._ptr = None
             self.cap = 0
+
+    def trim(self, keep):
+        """Give page-locked memory back after an oversized window (the arena is grow-only otherwise)."""
+        if self.cap > keep:
+            self.release()
+
+
+_MF_HDR_FIXED, _MF_TRAILER = 32, 13
+
+
+def packed_size_hint(path, size):
+    """Decoded size of a packed CAS file WITHOUT reading its payload: exact for files this library wrote (the
+    members' index headers are walked with a few small reads), the ISIZE trailer (mod 4 GiB, last member only)
+    for foreign gzip, the file size for anything else.  Used to bound load windows by UNPACKED bytes."""
+    try:
+        with open(path, "rb", buffering=0) as f:
+            pos, total, members = 0, 0, 0
+            while pos < size:
+                f.seek(pos)
+                h = f.read(_MF_HDR_FIXED)
+                if len(h) < _MF_HDR_FIXED or h[:4] != b"\x1f\x8b\x08\x04" or h[12:14] != b"MF":
+                    break
+                raw_len, nc = struct.unpack_from("<II", h, 20)
+                idx = f.read(8 * nc)
+                if len(idx) < 8 * nc:
+                    break
+                payload = sum(struct.unpack_from("<I", idx, 8 * k)[0] for k in range(nc))
+                pos += _MF_HDR_FIXED + 72 * nc + payload + _MF_TRAILER
+                total += raw_len
+                members += 1
+            if members and pos >= size:
+                return total
+            if size >= 18:
+                f.seek(size - 4)
+                (isize,) = struct.unpack("<I", f.read(4))
+                return max(total + isize, size)
+    except OSError:
+        pass
+    return size
 
 
 class FileSource(object):
@@ -116,6 +158,15 @@ class UnpackError(Exception):
         super().__init__(capi.STATUS_TEXT.get(code, "error %d" % code))
 
 
+def _locked(method):
+    def guarded(self, *a, **kw):
+        with self._lock:
+            return method(self, *a, **kw)
+
+    guarded.__name__, guarded.__doc__ = method.__name__, method.__doc__
+    return guarded
+
+
 class GpuCodec(object):
     def __init__(self, devices=None, wave_bytes=None, lz=None):
         lib = capi.load()
@@ -139,6 +190,22 @@ class GpuCodec(object):
         self._ctx = ctypes.c_void_p(ctx)
         self._in = _PinnedArena(lib)
         self._out = _PinnedArena(lib)
+        # The page-locked arenas are shared by every call: the views a call returns (Packed, decoded memoryviews)
+        # point into them and die with the next call.  Callers that keep views across statements -- the
+        # content-addressed store writes files from them, the task datastore unpickles from them -- hold
+        # `session()` for as long as they use the views; every codec method takes the same (re-entrant) lock.
+        self._lock = threading.RLock()
+
+    def session(self):
+        """Context manager: exclusive use of the codec and its arenas (re-entrant per thread)."""
+        return self._lock
+
+    def trim(self, keep=None):
+        """Release page-locked arenas larger than `keep` bytes (default METAFLOW_GPU_CAS_ARENA_KEEP)."""
+        keep = int(metaflow_config.GPU_CAS_ARENA_KEEP) if keep is None else keep
+        with self._lock:
+            self._in.trim(keep)
+            self._out.trim(keep)
 
     def close(self):
         if getattr(self, "_ctx", None):
@@ -215,6 +282,7 @@ class GpuCodec(object):
         return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
 
     # ------------------------------------------------------------------ save side
+    @_locked
     def hash_batch(self, blobs):
         """-> list of 40-hex SHA-1 keys (content_addressed_store.py:98)."""
         n = len(blobs)
@@ -228,6 +296,7 @@ class GpuCodec(object):
         raw = sha.tobytes()
         return [raw[20 * i:20 * i + 20].hex() for i in range(n)]
 
+    @_locked
     def pack_batch(self, blobs):
         """-> (keys, packed): packed[i] is a `Packed` (views over page-locked memory holding the RFC 1952
         bytes of blob i, one view per 2 MiB stripe).  Valid until the next pack/unpack call.
@@ -269,6 +338,7 @@ class GpuCodec(object):
             k += c
         return keys, packed
 
+    @_locked
     def pack_batch_contiguous(self, blobs):
         """Same result through mfcas_pack_batch: one contiguous view per blob (blob-granular waves)."""
         n = len(blobs)
@@ -313,6 +383,7 @@ class GpuCodec(object):
 
     accepts_file_sources = True
 
+    @_locked
     def unpack_batch(self, packed_blobs, as_bytes=True):
         """-> list with, per blob, the decoded bytes (or a memoryview over pinned memory when
         as_bytes=False, valid until the next call) or an UnpackError instance.
@@ -376,11 +447,21 @@ class GpuCodec(object):
 
 
 _default = None
+_forked_from_gpu_parent = False
 
 
 def default_codec():
-    """Process-wide GpuCodec; raises GpuCasUnavailable when the GPU path cannot run."""
+    """Process-wide codec; raises GpuCasUnavailable when the GPU path cannot run.  With
+    METAFLOW_GPU_CAS_SERVER set (a batcher daemon, or a parent that forked us through
+    multicore_utils.parallel_map) it is a RemoteCodec: this process never creates a CUDA context."""
     global _default
     if _default is None:
-        _default = GpuCodec()
+        from . import batcher
+
+        if os.environ.get(batcher.SERVER_ENV):
+            _default = batcher.RemoteCodec()
+        elif _forked_from_gpu_parent:
+            raise GpuCasUnavailable("forked from a process that owns the GPU context and no batcher is reachable")
+        else:
+            _default = GpuCodec()
     return _default

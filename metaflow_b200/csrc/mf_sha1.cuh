@@ -171,8 +171,9 @@ __device__ __forceinline__ void mf_sha_produce(MfShaSmem &S, const MfShaLane &L,
 }
 
 // ------------------------------------------------------------------ consumer of unit UNIT
+template <int VARIANT>
 __device__ __forceinline__ void mf_sha_consume(MfShaSmem &S, const MfShaLane &L, const uint32_t UNIT, const MfHashDesc *desc, uint32_t lane,
-                                               uint8_t *__restrict__ digests, unsigned long long *dbg_out) {
+                                               uint8_t *__restrict__ digests, unsigned long long *dbg_out, const uint32_t one, const uint32_t k30) {
     uint32_t h0 = 0x67452301u, h1 = 0xEFCDAB89u, h2 = 0x98BADCFEu, h3 = 0x10325476u, h4 = 0xC3D2E1F0u;
     if (L.valid && !L.is_first) {               // continue a message hashed piecewise (striped upload)
         const uint32_t *st = desc->state;
@@ -190,10 +191,22 @@ __device__ __forceinline__ void mf_sha_consume(MfShaSmem &S, const MfShaLane &L,
         // T = f + (e + (K+W)) is at least one round old; the chain is a' = rol(a,5) + T (LEA.HI).
         // The additions are pinned in PTX: left to the compiler, "+ f" is re-associated behind the
         // rotate-add and lands on the serial chain (LEA.HI -> IADD per round instead of LEA.HI alone).
+// VARIANT 0: T = IADD3(e, K+W, f) on the ALU pipe (4 ALU-pipe instructions per round: LOP3, IADD3, LEA.HI, SHF).
+// VARIANT 1: T by two IMADs with an opaque multiplier `one` (= 1, a kernel argument, so ptxas cannot fold them back
+//            into an IADD3): 3 ALU-pipe + 2 FMA-pipe instructions per round; the two pipes issue on alternate cycles.
+// VARIANT 3: rol(b,30) as IMAD.WIDE (b * 2^30: low word b<<30, high word b>>2) + IMAD: 3 ALU + 2 FMA, rotate off the ALU pipe.
 #define MF_RND(F, a, b, c, d, e, kw_) { uint32_t f_ = F(b, c, d); \
-        asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
-            : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
-        b = mf_rol(b, 30); }
+        if (VARIANT == 1) { \
+            asm("{\n\t.reg .u32 t_, r_;\n\tmad.lo.u32 t_, %1, %5, %2;\n\tmad.lo.u32 t_, %3, %5, t_;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
+                : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a), "r"(one)); \
+        } else { \
+            asm("{\n\t.reg .u32 t_, r_;\n\tadd.u32 t_, %1, %2;\n\tadd.u32 t_, t_, %3;\n\tshf.l.wrap.b32 r_, %4, %4, 5;\n\tadd.u32 %0, r_, t_;\n\t}" \
+                : "=r"(e) : "r"(e), "r"(kw_), "r"(f_), "r"(a)); \
+        } \
+        if (VARIANT == 3) { \
+            asm("{\n\t.reg .u64 p_;\n\t.reg .u32 lo_, hi_;\n\tmul.wide.u32 p_, %1, %2;\n\tmov.b64 {lo_, hi_}, p_;\n\tmad.lo.u32 %0, lo_, %3, hi_;\n\t}" \
+                : "=r"(b) : "r"(b), "r"(k30), "r"(one)); \
+        } else b = mf_rol(b, 30); }
 #define MF_RND20(F, q) { \
         uint4 k0 = kwv[5 * (q)], k1 = kwv[5 * (q) + 1], k2 = kwv[5 * (q) + 2], k3 = kwv[5 * (q) + 3], k4 = kwv[5 * (q) + 4]; \
         MF_RND(F, a, b, c, d, e, k0.x) MF_RND(F, e, a, b, c, d, k0.y) MF_RND(F, d, e, a, b, c, k0.z) MF_RND(F, c, d, e, a, b, k0.w) MF_RND(F, b, c, d, e, a, k1.x) \
@@ -231,8 +244,10 @@ __device__ __forceinline__ void mf_sha_consume(MfShaSmem &S, const MfShaLane &L,
 
 // digests: 20 bytes per blob in hashlib.sha1().digest() byte order.  dbg (optional): 4 counters per unit.
 // gate (optional): incremented once per CTA as soon as it is resident (see pack_submit).
+template <int VARIANT>
 __global__ void __launch_bounds__(MF_SHA_THREADS, 1) mf_sha1_kernel(const MfHashDesc *__restrict__ blobs, uint32_t n, uint8_t *__restrict__ digests,
-                                                                  unsigned long long *__restrict__ dbg, uint32_t *__restrict__ gate) {
+                                                                  unsigned long long *__restrict__ dbg, uint32_t *__restrict__ gate,
+                                                                  const uint32_t one, const uint32_t k30) {
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (gate && threadIdx.x == 0) atomicAdd(gate, 1u);
@@ -258,6 +273,6 @@ __global__ void __launch_bounds__(MF_SHA_THREADS, 1) mf_sha1_kernel(const MfHash
     for (int d = 16; d > 0; d >>= 1) { uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, iters, d); iters = o > iters ? o : iters; }
     L.iters = iters;
     unsigned long long *dbg_out = dbg ? dbg + ((size_t)blockIdx.x * MF_SHA_UNITS + unit) * 4 : nullptr;
-    if (warp < 2) mf_sha_consume(S, L, unit, desc, lane, digests, dbg_out);
+    if (warp < 2) mf_sha_consume<VARIANT>(S, L, unit, desc, lane, digests, dbg_out, one, k30);
     else mf_sha_produce(S, L, unit, warp < 4 ? 0u : 1u, lane, dbg_out);
 }

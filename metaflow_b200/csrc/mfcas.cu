@@ -128,6 +128,7 @@ struct Carver {
     size_t take(size_t bytes, size_t align = 256) { off = align_up(off, align); size_t o = off; off += bytes; return o; }
 };
 
+#define MF_SHA_DEFAULT_VARIANT 0
 #define MF_RING 8
 // Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
 // takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
@@ -157,13 +158,15 @@ int device_setup(DeviceState &D) {
     CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
-    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_SHA_UNITS * sizeof(MfShaSmem))));
+    for (auto k : {mf_sha1_kernel<0>, mf_sha1_kernel<1>, mf_sha1_kernel<3>}) {
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_SHA_UNITS * sizeof(MfShaSmem))));
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
     // split differs, and re-splitting needs the SM idle -- with the driver's per-kernel default the hash CTAs wait
     // for the persistent encoder to drain whenever the encoder happens to be dispatched first.  Same split for both.
-    CU(cudaFuncSetAttribute(mf_sha1_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     mf_init_tables_kernel<<<2, 256, 0, D.ring[0].stream>>>();
     CU(cudaGetLastError());
@@ -376,7 +379,11 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     unsigned long long *sha_dbg = nullptr;
     if (phase_timing_on()) { CU(W.phase2.ensure((size_t)sha_ctas * MF_SHA_UNITS * 4 * sizeof(unsigned long long))); sha_dbg = W.phase2.as<unsigned long long>(); }
     W.sha_ctas = sha_ctas;
-    mf_sha1_kernel<<<sha_ctas, MF_SHA_THREADS, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, gate);
+    {
+        static const int variant = getenv("MFCAS_SHA_VARIANT") ? atoi(getenv("MFCAS_SHA_VARIANT")) : MF_SHA_DEFAULT_VARIANT;
+        auto kern = variant == 1 ? mf_sha1_kernel<1> : variant == 3 ? mf_sha1_kernel<3> : mf_sha1_kernel<0>;
+        kern<<<sha_ctas, MF_SHA_THREADS, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, gate, 1u, 1u << 30);
+    }
     CU(cudaGetLastError());
     D.launches++;
     CU(cudaEventRecord(W.ev[1], s2));

@@ -11,11 +11,13 @@ iterator is drained in windows, and each window goes through GpuCodec.pack_batch
 unpack_batch (SHA-1, DEFLATE, CRC-32, INFLATE on the GPUs, sharded round-robin across devices).
 """
 import os
-from collections import namedtuple
+from collections import OrderedDict, namedtuple
+from contextlib import nullcontext
 from io import BytesIO
 
 from ..exception import DataException
 from .. import metaflow_config
+from ..codec import packed_size_hint
 
 
 class ContentAddressedStore(object):
@@ -29,6 +31,11 @@ class ContentAddressedStore(object):
         self._codec = codec
         # bytes of raw blobs gathered before a GPU batch is issued
         self._window_bytes = int(metaflow_config.GPU_CAS_WINDOW_BYTES)
+        self._window_unpacked = int(metaflow_config.GPU_CAS_WINDOW_UNPACKED_BYTES)
+        self._window_blobs = int(metaflow_config.GPU_CAS_WINDOW_BLOBS)
+        # content -> key of the tiny blobs this store has already keyed (the ~14 control artifacts every task of a
+        # foreach saves: `True`, `None`, the step name ...): a repeat is answered without touching the GPU
+        self._small_keys = OrderedDict()
 
     # -- plumbing ----------------------------------------------------------------------
     @property
@@ -41,6 +48,20 @@ class ContentAddressedStore(object):
 
     def set_blob_cache(self, blob_cache):
         self._blob_cache = blob_cache
+
+    def _session(self, codec):
+        """Exclusive use of the codec's page-locked arenas while views into them are alive (see GpuCodec.session)."""
+        session = getattr(codec, "session", None)
+        return session() if session else nullcontext()
+
+    _SMALL = 4096          # blobs up to this size are deduplicated by content on the host before any GPU work
+    _SMALL_CACHE = 4096    # entries kept
+
+    def _remember_small(self, content, key):
+        cache = self._small_keys
+        cache[content] = key
+        if len(cache) > self._SMALL_CACHE:
+            cache.popitem(last=False)
 
     def _path_for(self, key):
         return self._storage_impl.path_join(self._prefix, key[:2], key)
@@ -87,21 +108,61 @@ class ContentAddressedStore(object):
                     to_write.append((path, blob_data, {"cas_raw": True, "cas_version": 1}))
                 self._write(to_write)
                 continue
-            if raw:
-                keys, payloads = self.codec.hash_batch(window), window
-            else:
-                keys, payloads = self.codec.pack_batch(window)
-            paths = [self._path_for(k) for k in keys]
-            present = storage.is_file(paths)  # dedup: existing keys are never rewritten (:107)
-            seen = set()
+            # ---- dedup BEFORE pack (content_addressed_store.py:98-107 hashes, then skips what exists): identical
+            # small blobs of the window collapse to one, blobs keyed earlier by this store need no GPU work at all,
+            # and only what is left goes to the codec.  Large blobs are hashed and packed in the same GPU pass.
+            n = len(window)
+            keys = [None] * n
+            cached, dup_of, first_of, todo = set(), {}, {}, []
+            for i, blob in enumerate(window):
+                if len(blob) <= self._SMALL:
+                    content = bytes(blob)
+                    known = self._small_keys.get(content)
+                    if known is not None:
+                        keys[i] = known
+                        cached.add(i)
+                        continue
+                    j = first_of.setdefault(content, i)
+                    if j != i:
+                        dup_of[i] = j
+                        continue
+                todo.append(i)
             meta = {"cas_raw": raw, "cas_version": 1}
-            for key, path, have, payload in zip(keys, paths, present, payloads):
-                results.append(self.save_blobs_result(uri=storage.full_uri(path) if raw else None, key=key))
-                if have or key in seen:
-                    continue
-                seen.add(key)
-                to_write.append((path, payload, meta))
-            self._write(to_write)
+            codec = self.codec if todo else None
+            lost = []
+            with self._session(codec):
+                payload_of = {}
+                if todo:
+                    sub = [window[i] for i in todo]
+                    sub_keys, sub_payloads = (codec.hash_batch(sub), sub) if raw else codec.pack_batch(sub)
+                    for i, k, pl in zip(todo, sub_keys, sub_payloads):
+                        keys[i], payload_of[i] = k, pl
+                    for content, i in first_of.items():
+                        self._remember_small(content, keys[i])
+                for i, j in dup_of.items():
+                    keys[i] = keys[j]
+                paths = [self._path_for(k) for k in keys]
+                present = storage.is_file(paths)  # existing keys are never rewritten (:107)
+                seen = set()
+                for i in range(n):
+                    results.append(self.save_blobs_result(uri=storage.full_uri(paths[i]) if raw else None, key=keys[i]))
+                    if present[i] or keys[i] in seen:
+                        continue
+                    seen.add(keys[i])
+                    if i in payload_of:
+                        to_write.append((paths[i], payload_of[i], meta))
+                    elif i in cached:
+                        lost.append(i)                   # keyed from the cache, but its file is not there (any more)
+                self._write(to_write)
+            if lost:
+                codec = self.codec
+                with self._session(codec):
+                    sub = [window[i] for i in lost]
+                    payloads = sub if raw else codec.pack_batch(sub)[1]
+                    self._write([(paths[i], pl, meta) for i, pl in zip(lost, payloads)])
+            trim = getattr(codec, "trim", None) if codec is not None else None
+            if trim:
+                trim()
         return results
 
     # -- load --------------------------------------------------------------------------
@@ -131,11 +192,11 @@ class ContentAddressedStore(object):
         if not pending:
             return
         per_blob_unpack = "_unpack_v1" in self.__dict__ or type(self)._unpack_v1 is not ContentAddressedStore._unpack_v1
-        read_files = getattr(storage, "read_files", None)
-        if getattr(self.codec, "accepts_file_sources", False):
-            read_files = self._file_sources          # the codec reads the files itself, into page-locked memory
         with storage.load_bytes(pending) as loaded:
-            window, window_bytes = [], 0          # (key, path_key, meta, file_path) of blobs to decode on the GPU
+            # (key, path_key, meta, file_path) of blobs to decode on the GPU.  A window is bounded by its packed
+            # bytes, by its DECODED bytes (a constant array inflates 1000x: the page-locked output arena and the
+            # unpickled objects scale with that, not with the file sizes) and by its blob count.
+            window, packed_bytes, unpacked_bytes = [], 0, 0
             for path_key, file_path, meta in loaded:
                 key = storage.path_split(path_key)[-1]
                 if force_raw or (meta and meta.get("cas_raw", False)):
@@ -168,13 +229,34 @@ class ContentAddressedStore(object):
                         self._blob_cache.store_key(key, blob)
                     yield [(key, blob, meta) if is_transfer else (key, blob)]
                     continue
+                size = os.path.getsize(file_path)
+                hint = packed_size_hint(file_path, size)
+                if window and (unpacked_bytes + hint > self._window_unpacked or len(window) >= self._window_blobs):
+                    for out in self._decode_window(window, is_transfer, as_bytes):
+                        yield out
+                    window, packed_bytes, unpacked_bytes = [], 0, 0
                 window.append((key, path_key, meta, file_path))
-                window_bytes += os.path.getsize(file_path)
-                if window_bytes >= self._window_bytes:
-                    yield list(self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes))
-                    window, window_bytes = [], 0
+                packed_bytes += size
+                unpacked_bytes += hint
+                if packed_bytes >= self._window_bytes:
+                    for out in self._decode_window(window, is_transfer, as_bytes):
+                        yield out
+                    window, packed_bytes, unpacked_bytes = [], 0, 0
             if window:
-                yield list(self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes))
+                for out in self._decode_window(window, is_transfer, as_bytes):
+                    yield out
+
+    def _decode_window(self, window, is_transfer, as_bytes):
+        """One GPU batch.  The codec is resolved only here (raw loads never need one), and its arenas stay
+        locked until the consumer has advanced past the yielded list (its blobs may be views into them)."""
+        codec = self.codec
+        read_files = self._file_sources if getattr(codec, "accepts_file_sources", False) \
+            else getattr(self._storage_impl, "read_files", None)
+        with self._session(codec):
+            yield list(self._flush_unpack(self._read_window(window, read_files), is_transfer, as_bytes))
+        trim = getattr(codec, "trim", None)
+        if trim:
+            trim()
 
     @staticmethod
     def _file_sources(paths):

@@ -1,6 +1,8 @@
 """Read-through wrapper used by `spin` (metaflow/datastore/spin_datastore.py:1-91): artifacts the
-user supplied override those of the original task's datastore; everything else is delegated."""
-from itertools import chain
+user supplied override those of the original task's datastore; everything else comes from the task that
+is being re-run.  `_objects` / `_info` are what TaskDataStore.persist copies into the new task
+(task_datastore.py:760-762): the original task's maps minus the control artifact `_transition` -- user
+supplied spin artifacts are NOT in them (they are re-saved by persist like any other attribute)."""
 
 
 class SpinTaskDatastore(object):
@@ -11,22 +13,34 @@ class SpinTaskDatastore(object):
         self._task = None
         self._objects = dict(orig_datastore._objects)
         self._info = dict(orig_datastore._info)
-        for name in self.spin_artifacts:
-            self._objects.setdefault(name, None)
+        for control in ("_transition",):
+            self._objects.pop(control, None)
+            self._info.pop(control, None)
 
     def __getitem__(self, name):
         if name in self.spin_artifacts:
             return self.spin_artifacts[name]
-        return self.orig_datastore[name]
+        try:
+            return self.orig_datastore[name]
+        except (KeyError, AttributeError) as e:
+            raise KeyError("Attribute '%s' not found in the previous execution of the tasks for `%s`."
+                           % (name, self.step_name)) from e
+
+    def is_none(self, name):
+        return self[name] is None
 
     def __contains__(self, name):
-        return name in self.spin_artifacts or name in self.orig_datastore
+        try:
+            self[name]
+            return True
+        except KeyError:
+            return False
 
     def get(self, name, default=None):
-        return self[name] if name in self else default
+        try:
+            return self[name]
+        except KeyError:
+            return default
 
     def items(self):
-        return chain(((k, None) for k in self.spin_artifacts), self.orig_datastore.items())
-
-    def __getattr__(self, name):
-        return getattr(self.orig_datastore, name)
+        return self._objects.items() if self._objects else {}

@@ -11,12 +11,11 @@ sibling task of a foreach -- is pickled and handed to ContentAddressedStore.save
 batched unpack.  The datastore on disk is the reference's, file for file.
 """
 import inspect
-import pickle
 from itertools import count
 
 from .datastore import FlowDataStore, Inputs
-from .datastore.datastore_set import ImmutableBlobCache
 from .exception import MetaflowException, UnpicklableArtifactException
+from .serializer import dumps_segments, loads_batch
 from .parameters import Parameter
 from .plugins.datastores.local_storage import LocalStorage
 from .tuple_util import ForeachFrame
@@ -53,7 +52,7 @@ def step(f):
 class FlowSpec(object):
     # attributes that never become artifacts (flowspec.py:276-289)
     _EPHEMERAL = {"_EPHEMERAL", "_NON_PARAMETERS", "_datastore", "_cached_input", "_graph", "_flow_state",
-                  "_steps", "index", "input"}
+                  "_steps", "index", "input", "_join_group"}
 
     def __init__(self, use_cli=False):
         self.name = self.__class__.__name__
@@ -66,6 +65,11 @@ class FlowSpec(object):
     # -- lazy artifacts: attribute misses are served from the input datastore (flowspec.py:599-605)
     def __getattr__(self, name):
         ds = self.__dict__.get("_datastore")
+        group = self.__dict__.get("_join_group")
+        if group is not None and ds is not None and name in ds:
+            group.fetch(name)                    # one batched load of `name` for ALL inputs of the join
+            if name in self.__dict__:
+                return self.__dict__[name]
         if ds is not None and name in ds:
             value = ds[name]
             setattr(self, name, value)
@@ -151,6 +155,50 @@ class _Task(object):
         self.flow = self.out_ds = None
 
 
+class _JoinGroup(object):
+    """Join fan-in (metaflow/task.py:252-279 + datastore_set.py:38-50): the first time ANY input of a join is asked
+    for artifact `name`, the artifact is loaded for ALL inputs with one batched GPU unpack -- a join that reads
+    `inp.x for inp in inputs` is one unpack_batch instead of N single-blob loads.  Lazy like the reference (an
+    artifact nobody touches is never decoded), bounded (`cap` bytes of pickles per fetch, else inputs load one by
+    one) and local to the join: no blob cache is left behind on the shared content-addressed store."""
+
+    def __init__(self, flow_datastore, flows, cap=None):
+        from . import metaflow_config
+
+        self.ca_store = flow_datastore.ca_store
+        self.flows = flows
+        self.cap = int(metaflow_config.GPU_CAS_WINDOW_UNPACKED_BYTES) if cap is None else cap
+        self.fetches = 0
+
+    def fetch(self, name):
+        holders = {}
+        for f in self.flows:
+            ds = f.__dict__.get("_datastore")
+            if ds is not None and name in ds and name not in f.__dict__:
+                holders.setdefault(ds._objects[name], []).append(f)
+        if len(holders) < 2 and sum(len(v) for v in holders.values()) < 2:
+            return                                   # nothing to batch: the ordinary single load follows
+        total = 0
+        for key, fs in holders.items():
+            total += len(fs) * fs[0]._datastore._info.get(name, {}).get("size", 0)
+        if total > self.cap:
+            return
+        self.fetches += 1
+        loader = getattr(self.ca_store, "_load_batches", None)
+        if loader is None:
+            batches = [list(self.ca_store.load_blobs(list(holders)))]
+        else:
+            batches = loader(list(holders), False, False, as_bytes=False)
+        for batch in batches:
+            targets, blobs = [], []
+            for key, blob in batch:
+                for f in holders[key]:               # every input gets its own freshly unpickled object
+                    targets.append(f)
+                    blobs.append(blob)
+            for f, obj in zip(targets, loads_batch(blobs)):
+                setattr(f, name, obj)
+
+
 class FlowRunner(object):
     """run = FlowRunner(MyFlow, ds_root=...).run(); the datastore it leaves behind is a Metaflow datastore."""
 
@@ -177,47 +225,58 @@ class FlowRunner(object):
         return self.flow_datastore.get_task_datastore(self.run_id, step_name, str(task_id), attempt=0)
 
     def _run_step_tasks(self, tasks, join_inputs=None):
-        """Run the user code of all sibling tasks of one step, then persist ALL their artifacts as ONE batch."""
+        """Run the user code of all sibling tasks of one step and persist ALL their artifacts through ONE
+        save_blobs call.  The call pulls a generator: a task's step function runs when the store asks for its
+        blobs, its artifacts are pickled by reference (serializer.dumps_segments, the same serialiser
+        TaskDataStore.save_artifacts uses) and leave the flow object right away (what persist does,
+        task_datastore.py:794-806), so at most one window of artifacts (GPU_CAS_WINDOW_BYTES) is alive at a time
+        however wide the foreach is."""
         fds = self.flow_datastore
-        staged = []                      # (task, names, blobs, infos)
-        for t in tasks:
-            t.out_ds = fds.get_task_datastore(self.run_id, t.step, str(t.task_id), attempt=0, mode="w")
-            t.out_ds.init_task()
-            t.flow = self._bind(t, t.input_ds)
-            fn = getattr(t.flow, t.step)
-            if join_inputs is not None:
-                fn(join_inputs)
-            else:
-                fn()
-            if t.flow._transition is None and t.step != "end":
-                raise InvalidNextException("Step *%s* does not call self.next()" % t.step)
-            if t.flow._transition is None:
-                t.flow._transition = ([], None)
-            out = t.out_ds
-            if t.input_ds is not None:                       # unchanged artifacts pass down by key, no re-save
-                out._objects.update(t.input_ds._objects)
-                out._info.update(t.input_ds._info)
-            for n, holder in t.flow.__dict__.pop("_merged_from", {}).items():
-                out.passdown_partial(holder._datastore, [n])
-            names, blobs = [], []
-            for var, val in sorted(t.flow.__dict__.items()):
-                if var.startswith("__") or var in FlowSpec._EPHEMERAL or isinstance(val, Parameter):
-                    continue
-                if var == "_foreach_stack_frames":
-                    continue
-                try:
-                    blob = pickle.dumps(val, protocol=4)
-                except TypeError as e:
-                    raise UnpicklableArtifactException(var) from e
-                out._info[var] = {"size": len(blob), "type": str(type(val)), "encoding": "gzip+pickle-v4"}
-                names.append(var)
-                blobs.append(blob)
-            staged.append((t, names, blobs))
-        # ---- the batcher: one save_blobs call for the step's whole artifact set
-        flat = [b for _, _, blobs in staged for b in blobs]
-        results = fds.ca_store.save_blobs(iter(flat), len_hint=len(flat))
+        staged = []                      # (task, names): which results belong to which task
+
+        def blobs():
+            for t in tasks:
+                t.out_ds = fds.get_task_datastore(self.run_id, t.step, str(t.task_id), attempt=0, mode="w")
+                t.out_ds.init_task()
+                t.flow = self._bind(t, t.input_ds)
+                fn = getattr(t.flow, t.step)
+                if join_inputs is not None:
+                    fn(join_inputs)
+                else:
+                    fn()
+                if t.flow._transition is None and t.step != "end":
+                    raise InvalidNextException("Step *%s* does not call self.next()" % t.step)
+                if t.flow._transition is None:
+                    t.flow._transition = ([], None)
+                out = t.out_ds
+                if t.input_ds is not None:                       # unchanged artifacts pass down by key, no re-save
+                    out._objects.update(t.input_ds._objects)
+                    out._info.update(t.input_ds._info)
+                for n, holder in t.flow.__dict__.pop("_merged_from", {}).items():
+                    out.passdown_partial(holder._datastore, [n])
+                names = []
+                keep = {t.flow._transition[1]}                   # the foreach variable is read again for the fan-out
+                for var, val in sorted(t.flow.__dict__.items()):
+                    if var.startswith("__") or var in FlowSpec._EPHEMERAL or isinstance(val, Parameter):
+                        continue
+                    if var == "_foreach_stack_frames":
+                        continue
+                    try:
+                        blob = dumps_segments(val)
+                    except TypeError as e:
+                        raise UnpicklableArtifactException(var) from e
+                    out._info[var] = {"size": len(blob), "type": str(type(val)), "encoding": "gzip+pickle-v4"}
+                    names.append(var)
+                    yield blob
+                for var in names:                                # hand-over: user artifacts leave the flow object
+                    if not var.startswith("_") and var != "name" and var not in keep:
+                        del t.flow.__dict__[var]
+                staged.append((t, names))
+
+        # ---- the batcher: one save_blobs call for the step's whole artifact set (windowed inside the store)
+        results = fds.ca_store.save_blobs(blobs(), len_hint=len(tasks))
         pos = 0
-        for t, names, blobs in staged:
+        for t, names in staged:
             for n in names:
                 t.out_ds._objects[n] = results[pos].key
                 pos += 1
@@ -292,21 +351,12 @@ class FlowRunner(object):
                 join_batch.append((jt, members))
             # every join task of this step is its own batch entry: its inputs differ
             for jt, members in join_batch:
-                dss = [ds for _, ds in members]
-                self._prefetch(dss)
-                frontier.append((nxt, [jt], Inputs(self._bind(t, ds) for t, ds in members)))
+                flows = [self._bind(t, ds) for t, ds in members]
+                group = _JoinGroup(self.flow_datastore, flows)
+                for f in flows:
+                    f._join_group = group
+                frontier.append((nxt, [jt], Inputs(flows)))
         return self
-
-    def _prefetch(self, datastores):
-        """Join fan-in (metaflow/task.py:252-279 + datastore_set.py:38-50, widened to user artifacts): every
-        distinct key the inputs hold is decoded in ONE batched GPU unpack and served from a blob cache."""
-        keys = set()
-        for ds in datastores:
-            keys.update(k for n, k in ds.items() if not n.startswith("_"))
-        keys.discard(None)
-        cas = self.flow_datastore.ca_store
-        cas.set_blob_cache(None)
-        cas.set_blob_cache(ImmutableBlobCache(dict(cas.load_blobs(keys))))
 
     def task_datastores(self, step_name):
         return self.finished[step_name]

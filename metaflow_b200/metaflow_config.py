@@ -36,6 +36,11 @@ GPU_CAS_WAVE_BYTES = from_conf("GPU_CAS_WAVE_BYTES", 1 << 30)  # bytes (in + out
 # blob (~8 ms per MiB on a GPU lane), so a call is only as fast as it is WIDE: the window should hold as many
 # blobs as the caller has (the page-locked staging arenas grow on demand up to in + out of this size).
 GPU_CAS_WINDOW_BYTES = from_conf("GPU_CAS_WINDOW_BYTES", 4 << 30)
+# load windows are also bounded by their DECODED size and blob count (highly compressible artifacts inflate 1000x)
+GPU_CAS_WINDOW_UNPACKED_BYTES = from_conf("GPU_CAS_WINDOW_UNPACKED_BYTES", 8 << 30)
+GPU_CAS_WINDOW_BLOBS = from_conf("GPU_CAS_WINDOW_BLOBS", 1 << 17)
+# page-locked staging arenas larger than this are released after the window that needed them
+GPU_CAS_ARENA_KEEP = from_conf("GPU_CAS_ARENA_KEEP", 12 << 30)
 GPU_CAS_LZ = from_conf("GPU_CAS_LZ", 1)                        # 0 = Huffman-only encoder
 
 # client-side file cache (metaflow/metaflow_config.py:113-121)

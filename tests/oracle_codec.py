@@ -7,6 +7,7 @@ from oracle import ref_path
 class OracleCodec(object):
     def __init__(self):
         self.calls = {"pack": 0, "hash": 0, "unpack": 0}
+        self.packed_blobs = 0
 
     def hash_batch(self, blobs):
         self.calls["hash"] += 1
@@ -14,6 +15,7 @@ class OracleCodec(object):
 
     def pack_batch(self, blobs):
         self.calls["pack"] += 1
+        self.packed_blobs += len(blobs)
         return [ref_path.blob_key(bytes(b)) for b in blobs], [memoryview(ref_path.pack_v1(bytes(b), mtime=0)) for b in blobs]
 
     def unpack_batch(self, packed, as_bytes=True):

@@ -92,3 +92,69 @@ def test_eviction_oldest_first_with_quarantine(tmp_path, monkeypatch):
 def test_unknown_datastore_type(tmp_path):
     with pytest.raises(filecache.FileCacheException):
         FileCache(cache_dir=str(tmp_path))._get_flow_datastore("s3", "s3://bucket/x", "F")
+
+
+def test_client_object_model_over_a_flow_run(tmp_path):
+    """Flow / Run / Step / Task / DataArtifact / MetaflowData (client/core.py:973, 1106, 1511, 2257) over a
+    datastore an in-process run left behind; Step.artifacts fetches a whole foreach step with ONE batched load."""
+    import textwrap
+    from oracle_codec import OracleCodec
+    from metaflow_b200 import client
+    from metaflow_b200.client import FileCache, Flow, Run, Step, Task
+    from metaflow_b200.flowspec import FlowRunner
+
+    src = textwrap.dedent("""
+        import numpy as np
+        from metaflow_b200.flowspec import FlowSpec, step
+        class ClientFlow(FlowSpec):
+            @step
+            def start(self):
+                self.items = [3, 5, 7, 11]
+                self.next(self.work, foreach="items")
+            @step
+            def work(self):
+                self.vec = np.full(5000, self.input, dtype=np.float32)
+                self.next(self.join)
+            @step
+            def join(self, inputs):
+                self.total = float(sum(float(i.vec[0]) for i in inputs))
+                self.next(self.end)
+            @step
+            def end(self):
+                self.answer = self.total * 2
+    """)
+    ns = {}
+    exec(compile(src, "clientflow.py", "exec"), ns)
+    codec = OracleCodec()
+    root = str(tmp_path / "ds")
+    FlowRunner(ns["ClientFlow"], ds_root=root, codec=codec).run()
+    client.set_datastore_root(root)
+    client.set_filecache(FileCache(cache_dir=str(tmp_path / "cache"), max_size=100, codec=codec))
+    try:
+        flow = Flow("ClientFlow")
+        run = flow.latest_run
+        assert run.id == "1" and run.finished and run.successful is False      # the in-process runner writes no _task_ok
+        assert {s.id for s in run} == {"start", "work", "join", "end"}
+        assert run.data.answer == 52.0 and "answer" in run.data and "nope" not in run.data
+        step = Step("ClientFlow/1/work")
+        tasks = step.tasks()
+        assert len(tasks) == 4 and all(isinstance(t, Task) for t in tasks)
+        calls0 = codec.calls["unpack"]
+        got = step.artifacts(["vec"])
+        assert codec.calls["unpack"] == calls0 + 1                             # four tasks, one batched decode
+        assert sorted(float(v["vec"][0]) for v in got.values()) == [3.0, 5.0, 7.0, 11.0]
+        t = tasks[0]
+        assert t.index in (0, 1, 2, 3) and t.finished and t.current_attempt == 0
+        calls1 = codec.calls["unpack"]                                         # (index read `_foreach_stack`)
+        art = t["vec"]
+        assert art.sha == t._meta()["objects"]["vec"] and art.size > 20000 and art.data.shape == (5000,)
+        assert codec.calls["unpack"] == calls1                                 # ... served from the cache files now
+        d = t.data
+        assert float(d.vec[0]) in (3.0, 5.0, 7.0, 11.0) and [a.id for a in t] == sorted(a.id for a in t)
+        assert Run("ClientFlow/1")["join"].task.data.preload().total == 26.0
+        import pytest as _pytest
+        with _pytest.raises(client.MetaflowNotFound):
+            Task("ClientFlow/1/work/999")
+    finally:
+        client.set_datastore_root(None)
+        client.set_filecache(None)

@@ -54,9 +54,17 @@ def test_one_gpu_batch_per_window_and_dedup(fds, tmp_path):
     assert codec.calls["pack"] == 1                      # whole iterator -> one batch
     assert len({r.key for r in res}) == 2 and [r.key for r in res][:5] == [res[0].key] * 5
     before = {p: p.stat().st_mtime_ns for p in (tmp_path / "GoldenFlow" / "data").rglob("*") if p.is_file()}
-    fds.ca_store.save_blobs(iter(blobs))                 # existing keys are never rewritten
+    res_again = fds.ca_store.save_blobs(iter(blobs))     # existing keys are never rewritten ...
     after = {p: p.stat().st_mtime_ns for p in (tmp_path / "GoldenFlow" / "data").rglob("*") if p.is_file()}
-    assert before == after
+    assert before == after and res_again == res
+    assert codec.calls["pack"] == 1                      # ... and tiny blobs keyed before cost no codec call at all
+    # dedup happens BEFORE pack: only the two distinct blobs ever reached the codec
+    assert codec.packed_blobs == 2
+    # a key remembered from earlier whose file has vanished is packed and written again
+    victim = tmp_path / "GoldenFlow" / "data" / res[0].key[:2] / res[0].key
+    victim.unlink()
+    assert fds.ca_store.save_blobs(iter([b"same"]))[0].key == res[0].key and victim.is_file()
+    assert codec.calls["pack"] == 2
     fds.ca_store._window_bytes = 8                       # small window -> several batches, same result
     res2 = fds.ca_store.save_blobs(iter([b"0123456789", b"abcdefghij", b"xyz"]))
     assert codec.calls["pack"] == 2 + 3
