@@ -35,9 +35,16 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 import numpy as np  # noqa: E402
 
-ARRAY_ELEMS = 4194304            # 16 MiB of float32
+ARRAY_ELEMS = 4194304            # 16 MiB of float32 (config C2; --config C3 / C4 change it)
 METRIC = "artifact_roundtrip_GBps"
 UNIT = "GB/s"
+
+# BASELINE.json configs that fit one GPU: elements per fp32 artifact, blobs per step per GPU, what it is
+CONFIGS = {
+    "C2": (4194304, 2048, "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts"),
+    "C3": (16384, 65536, "C3 foreach x65536, 64 KiB fp32 N(0,1) artifacts (hash-bound small-blob path)"),
+    "C4": (262144, 16384, "C4 nested foreach 256x256, 1 MiB fp32 N(0,1) artifacts, join loads (65536 leaves = 4 steps)"),
+}
 
 
 def pickle_frame(n_elems):
@@ -161,11 +168,11 @@ def run_reference(args, rank, world):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * (tot_s + tot_l) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "impl": "reference",
-        "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts, save_blobs+load_blobs", "sample": "%d blobs/step (%d procs x %d)" % (cores * per, cores, per),
+        "config": {"workload": "%s, save_blobs+load_blobs" % args.workload, "name": args.config, "sample": "%d blobs/step (%d procs x %d)" % (cores * per, cores, per),
                    "datastore": "local on tmpfs"},
         "save_GBps": tot_b / tot_s / 1e9, "load_GBps": tot_b / tot_l / 1e9,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
-                         "sample": "%d x 16 MiB blobs per step through oracle/ref_path.py (hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files), process per task" % (cores * per)},
+                         "sample": "%d blobs per step through oracle/ref_path.py (hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files), process per task" % (cores * per)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -266,7 +273,12 @@ def run_ours(args, rank, world, local_rank):
     for w in range(max(1, args.warmup)):      # at least one untimed pass: it is also the parity gate
         generate(10_000 + w)
         step_device()
-    verify(sorted(set([0, n // 2, n - 1])))
+    # parity gate: every blob for the small-blob config, >= 1 % of the step otherwise -- keys against
+    # hashlib, our files through the reference's reader (CPython gzip), decoded bytes against the inputs
+    n_check = n if args.config == "C3" else max(3, int(n * args.verify_frac + 0.999))
+    picks = np.random.default_rng(1234 + rank).choice(n, size=min(n, n_check), replace=False)
+    verify(sorted(set(int(i) for i in picks) | {0, n - 1}))
+    verified = len(set(int(i) for i in picks) | {0, n - 1})
 
     # ---- HBM-resident timed steps
     counters0 = [u64(0), u64(0), u64(0)]
@@ -288,7 +300,9 @@ def run_ours(args, rank, world, local_rank):
     counters1 = [u64(0), u64(0), u64(0)]
     lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in counters1])
     launches = counters1[0].value - counters0[0].value
-    verify([1])
+    picks = np.random.default_rng(4321 + rank).choice(n, size=min(n, max(3, int(n * args.verify_frac + 0.999))), replace=False)
+    verify(sorted(int(i) for i in picks))               # and again on the last timed step's output
+    verified += len(picks)
     raw_bytes = args.steps * n * blob_len
 
     # ---- end-to-end through the host-pointer C ABI (pinned host buffers, copies timed).
@@ -301,8 +315,10 @@ def run_ours(args, rank, world, local_rank):
     estride = (ecap + 255) // 256 * 256 + 256
     # the step's blobs go through the host API in sub-batches of <= 1024 (17 GB): the path is PCIe-bound, so its
     # rate does not depend on the batch, and the page-locked buffers stay at 3 x 17 GB per rank
-    ne = min(n, 1024)
-    assert n % ne == 0, "--blobs-per-step must be a multiple of 1024 (or smaller than it)"
+    ne = n
+    while ne * stride > (18 << 30) and ne % 2 == 0:
+        ne //= 2
+    assert n % ne == 0
     h_in_p = lib.mfcas_alloc_pinned(ne * stride); h_pk_p = lib.mfcas_alloc_pinned(ne * estride); h_out_p = lib.mfcas_alloc_pinned(ne * stride)
     assert h_in_p and h_pk_p and h_out_p, "pinned allocation failed"
     h_in = np.ctypeslib.as_array((ctypes.c_uint8 * (ne * stride)).from_address(h_in_p))
@@ -446,13 +462,14 @@ def run_ours(args, rank, world, local_rank):
             cpu_reference_pass(cores, 1, 99)
             b, ts, tl = cpu_reference_pass(cores, per, 5_000_000)
             cpu = {"value": b / (ts + tl) / 1e9, "unit": UNIT, "cores": cores, "logical_cpus": os.cpu_count(), "kind": "port",
-                   "sample": "%d x 16 MiB blobs (%d procs x %d) through oracle/ref_path.py: hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files" % (cores * per, cores, per),
+                   "sample": "%d blobs (%d procs x %d) through oracle/ref_path.py: hashlib.sha1 + gzip level 3 + gunzip + tmpfs CAS files" % (cores * per, cores, per),
                    "save_GBps": b / ts / 1e9, "load_GBps": b / tl / 1e9}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": (t_save + t_load) / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C2 foreach x4096, 16 MiB fp32 N(0,1) artifacts (pickle blob %d B), save+load" % blob_len,
+            "config": {"workload": "%s (pickle blob %d B), save+load" % (args.workload, blob_len), "name": args.config,
+                       "verified_blobs": verified,
                        "blobs_per_step_per_gpu": n, "blobs_total": n * args.steps * world, "sharding": "round-robin blob i -> rank i mod N, no collective",
                        "l2": "inputs %.1f GB per step >> 126 MB L2 (no flush needed)" % (n * blob_len / 1e9), "packed_ratio": ratio,
                        "e2e_sub_batch": ne, "wave_mib": args.wave_mib},
@@ -481,12 +498,20 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blobs-per-step", type=int, default=2048)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS), help="BASELINE.json config (the driver's default run is C2)")
+    ap.add_argument("--blobs-per-step", type=int, default=0, help="0 = the config's own wave size")
+    ap.add_argument("--verify-frac", type=float, default=0.01, help="fraction of every verified step's blobs checked against the oracle")
     ap.add_argument("--wave-mib", type=int, default=1024, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--api-blobs", type=int, default=64, help="artifacts in the L-api (objects <-> tmpfs files) sample; 0 = skip")
     args = ap.parse_args()
+    global ARRAY_ELEMS
+    ARRAY_ELEMS = CONFIGS[args.config][0]
+    if args.blobs_per_step <= 0:
+        args.blobs_per_step = CONFIGS[args.config][1]
+    args.workload = CONFIGS[args.config][2]
+    args.ref_blobs_per_proc *= max(1, 4194304 // ARRAY_ELEMS)        # the CPU sample stays about 64 MiB per process
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -35,3 +35,14 @@ def raw_blobs():
         "random_5000": rng.bytes(5000),
         "ramp_70000": bytes(range(256)) * 273 + b"xyz",
     }
+
+
+def large_artifacts():
+    """name -> 16 MiB fp32 array (pickle blob 16,777,379 B) saved by the REAL reference in oracle/make_golden_large.py."""
+    n = 4194304
+    rng = np.random.default_rng(77)
+    lowent = rng.integers(0, 16, n).astype(np.float32)
+    sparse = np.zeros(n, dtype=np.float32)
+    for k in range(0, n, 16384):                       # a 2 KiB stripe of noise at the start of every 64 KiB
+        sparse[k:k + 512] = rng.standard_normal(512, dtype=np.float32)
+    return {"lowent_16mib": lowent, "sparse_16mib": sparse}
