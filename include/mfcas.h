@@ -118,6 +118,16 @@ int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n,
                       const void *const *d_src, const uint64_t *src_len,
                       void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len,
                       uint8_t *sha1, int32_t *status);
+/* Device-resident form of mfcas_pack_batch_extents: member m of blob i (its m-th 2 MiB stripe) is written straight
+ * to d_dst[i] + ext_off[..] by the encoder -- no scratch, no compaction pass; dst_cap[i] >= mfcas_pack_extent_bound.
+ * mfcas_compact_device then moves the extents of every blob together IN PLACE (what writev() into the CAS file does
+ * on the host path) so that d_dst[i][0 .. dst_len[i]) is the contiguous RFC 1952 file mfcas_unpack_device takes. */
+int mfcas_pack_device_extents(mfcas_ctx *ctx, int dev_slot, uint64_t n,
+                              const void *const *d_src, const uint64_t *src_len,
+                              void *const *d_dst, const uint64_t *dst_cap,
+                              uint64_t *ext_off, uint64_t *ext_len, uint8_t *sha1, int32_t *status);
+int mfcas_compact_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, void *const *d_dst, const uint64_t *src_len,
+                         const uint64_t *ext_len, uint64_t *dst_len);
 int mfcas_unpack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n,
                         const void *const *d_src, const uint64_t *src_len,
                         void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len,

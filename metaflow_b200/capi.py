@@ -47,6 +47,8 @@ SIGNATURES = [
     ("mfcas_unpacked_size", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _u64p, ctypes.POINTER(ctypes.c_int)]),
     ("mfcas_unpack_batch", ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, _i32p]),
     ("mfcas_pack_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, ctypes.c_void_p, _i32p]),
+    ("mfcas_pack_device_extents", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, _u64p, ctypes.c_void_p, _i32p]),
+    ("mfcas_compact_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, _vpp, _u64p, _u64p, _u64p]),
     ("mfcas_unpack_device", ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, _vpp, _u64p, _vpp, _u64p, _u64p, _i32p]),
     ("mfcas_stream", ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
     ("mfcas_counters", None, [ctypes.c_void_p, _u64p, _u64p, _u64p]),

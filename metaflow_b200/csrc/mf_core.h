@@ -50,13 +50,14 @@ static inline uint32_t mf_brev_host(uint32_t v) {
 //             stored block (00 00 00 FF FF after bit padding), so every chunk ends byte-aligned.
 //   segment = 1 KiB of raw bytes   = the LZ77 window (matches never leave their segment) and the
 //             unit one decoder lane decodes; its token bit length is in the index.
-//   member  = up to 768 chunks (24 MiB raw); ends with a final empty stored block 01 00 00 FF FF.
+//   member  = up to 64 chunks (2 MiB raw: one stripe, the unit one encoder CTA owns); ends with a final empty
+//             stored block 01 00 00 FF FF.
 #define MF_CHUNK_LOG2 15
 #define MF_CHUNK (1u << MF_CHUNK_LOG2)
 #define MF_SEG_LOG2 10
 #define MF_SEG (1u << MF_SEG_LOG2)
 #define MF_SEGS_PER_CHUNK (MF_CHUNK / MF_SEG)       // 32
-#define MF_MEMBER_CHUNKS 768u
+#define MF_MEMBER_CHUNKS 64u
 #define MF_MEMBER_RAW ((uint64_t)MF_MEMBER_CHUNKS * MF_CHUNK)
 #define MF_HDR_FIXED 32u                              // 10 gzip + 2 XLEN + 4 subfield hdr + 16 payload hdr
 #define MF_IDX_PER_CHUNK 72u                          // 8 (comp_bytes u32, hdr_bits u16, rsv u16) + 32*2 seg bits

@@ -246,7 +246,7 @@ MF_HD uint64_t mf_is_indexed_member(const uint8_t *p, uint64_t n, uint32_t *raw_
     if (p[12] != 'M' || p[13] != 'F') return 0;
     if (p[16] != MF_FORMAT_VERSION || p[17] != MF_CHUNK_LOG2 || p[18] != MF_SEG_LOG2) return 0;
     uint32_t rl = mf_le32(p + 20), nc = mf_le32(p + 24);
-    if (nc > MF_MEMBER_CHUNKS || nc != (uint32_t)mf_n_chunks(rl)) return 0;
+    if (nc > 768u || nc != (uint32_t)mf_n_chunks(rl)) return 0;      // writers: 64 chunks per member (768 in format revision 0)
     uint64_t hdr = mf_member_header_bytes(nc);
     if (mf_le16(p + 10) != hdr - 12 || mf_le16(p + 14) != hdr - 16 || hdr > n) return 0;
     *raw_len = rl; *n_chunks = nc;

@@ -23,9 +23,10 @@
 #include "mf_core.h"
 #include "mf_sha1.cuh"
 #include "mf_deflate.cuh"
+#include "mf_deflate2.cuh"
 #include "mf_inflate.cuh"
 
-#define MFCAS_VERSION_STR "mfcas 0.1 (sm_100a; format MF v1: chunk 32 KiB, segment 1 KiB)"
+#define MFCAS_VERSION_STR "mfcas 0.2 (sm_100a; format MF v1: chunk 32 KiB, segment 1 KiB, member 2 MiB)"
 
 namespace {
 
@@ -74,7 +75,7 @@ struct WaveCtx {
     // bookkeeping of the submitted wave
     int state = 0;                       // 0 idle, 1 kernels in flight, 2 output D2H in flight
     Op op = Op::Pack;
-    uint64_t n = 0, n_chunks = 0;
+    uint64_t n = 0, n_out = 0, n_chunks = 0;
     unsigned sha_ctas = 0;
     size_t r_len = 0, r_st = 0, r_sha = 0, res_bytes = 0;
     bool timed_pack = false;
@@ -163,12 +164,16 @@ int device_setup(DeviceState &D) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
+    CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEnc2Smem)));
+    CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
     // split differs, and re-splitting needs the SM idle -- with the driver's per-kernel default the hash CTAs wait
     // for the persistent encoder to drain whenever the encoder happens to be dispatched first.  Same split for both.
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     mf_init_tables_kernel<<<2, 256, 0, D.ring[0].stream>>>();
+    CU(cudaGetLastError());
+    mf_init_tables2_kernel<<<4, 256, 0, D.ring[0].stream>>>();
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(D.ring[0].stream));
     return MFCAS_OK;
@@ -259,28 +264,39 @@ static bool phase_timing_on() { static const bool on = getenv("MFCAS_PHASE_TIMIN
 // that nothing small ever queues behind other waves' gigabyte copies on the copy engine.
 // `chain` (striped packing): SHA-1 descriptors of message PIECES (state carried across waves); `sha_deps` are
 // the ev_sha events of the in-flight waves that hold the previous piece of any of these blobs.
+// Where the encoder's members go:
+//   PackContiguous  one contiguous RFC 1952 file per blob in d_dst[i]: members are encoded into scratch slots and moved
+//                   together by the compaction kernels (mfcas_pack_batch, mfcas_pack_device)
+//   PackUnits       every unit IS one member (a stripe of the striped host API): written straight to d_dst[k]
+//   PackSlots       device-resident extents: member m of blob i is written straight to d_dst[i] + m * ext_slot();
+//                   results (length, status) are per MEMBER, blob-major
+enum PackLayout { PackContiguous = 0, PackUnits = 1, PackSlots = 2 };
+inline uint64_t ext_slot_bytes() { return align_up(mf_pack_bound(MF_MEMBER_RAW), 256); }
+static bool enc_v1() { static const bool on = getenv("MFCAS_ENC") != nullptr && atoi(getenv("MFCAS_ENC")) == 1; return on; }
+
 int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const void *const *d_src, const uint64_t *src_len,
                 void *const *d_dst, const uint64_t *dst_cap, bool want_pack, const CopyPlan *upload,
-                const MfHashDesc *chain = nullptr, const std::vector<cudaEvent_t> *sha_deps = nullptr) {
+                const MfHashDesc *chain = nullptr, const std::vector<cudaEvent_t> *sha_deps = nullptr, PackLayout layout = PackContiguous) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
+    const bool v1 = enc_v1() && layout != PackSlots;
     uint64_t n_members = 0, n_chunks = 0;
     if (want_pack)
         for (uint64_t i = 0; i < n; i++) { n_members += mf_n_members(src_len[i]); n_chunks += mf_n_chunks(src_len[i]); }
-    const uint64_t max_groups = n_chunks / MF_ENC_GROUP + n_members;      // encoder work units: <= MF_ENC_GROUP chunks of one member
-    if (n_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
+    if (layout == PackUnits && n_members != n) return MFCAS_E_ARG;           // a unit is at most one stripe
+    const uint64_t max_groups = n_chunks / MF_ENC_GROUP + n_members;      // v1 encoder work units: <= MF_ENC_GROUP chunks of one member
+    if (n_chunks > 0x7FFFFFF0ull || n_members > 0x7FFFFFF0ull) return MFCAS_E_ARG;
+    const uint64_t n_out = (want_pack && layout == PackSlots) ? n_members : n;   // entries of the length / status result arrays
     Carver hc;
     const size_t o_hash = hc.take(sizeof(MfHashDesc) * n);
-    const size_t o_blob = hc.take(sizeof(MfEncBlob) * n);
-    const size_t o_mem = hc.take(sizeof(MfEncMember) * n_members);
-    const size_t o_cm = hc.take(sizeof(uint32_t) * n_chunks);
+    const size_t o_blob = hc.take(std::max(sizeof(MfEncBlob), sizeof(MfCompactBlob)) * n);
+    const size_t o_mem = hc.take(std::max(sizeof(MfEncMember), sizeof(MfEnc2Member)) * n_members);
+    const size_t o_cm = hc.take(sizeof(uint32_t) * (v1 ? n_chunks : n_members));      // v1: chunk -> member; v2: member -> blob
     const size_t o_grp = hc.take(sizeof(uint32_t) * max_groups);
     const size_t desc_bytes = hc.take(0);
     CU(W.h_desc.ensure(desc_bytes));
     CU(W.d_desc.ensure(desc_bytes));
     uint8_t *hd = W.h_desc.as<uint8_t>();
     MfHashDesc *h_hash = reinterpret_cast<MfHashDesc *>(hd + o_hash);
-    MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
-    MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
     uint32_t *h_cm = reinterpret_cast<uint32_t *>(hd + o_cm);
     uint32_t *h_grp = reinterpret_cast<uint32_t *>(hd + o_grp);
     uint32_t n_groups = 0;
@@ -300,8 +316,12 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             h_hash[k].state = nullptr;
         }
     }
+    const uint64_t slot_stride = ext_slot_bytes();
+    if (want_pack && !v1 && layout == PackContiguous) CU(W.slots.ensure((size_t)n_members * slot_stride + 256));
     uint32_t mi = 0, ci = 0;
-    if (want_pack) {
+    if (want_pack && v1) {
+        MfEncBlob *h_blob = reinterpret_cast<MfEncBlob *>(hd + o_blob);
+        MfEncMember *h_mem = reinterpret_cast<MfEncMember *>(hd + o_mem);
         for (uint64_t i = 0; i < n; i++) {
             h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
             h_blob[i].dst_cap = dst_cap[i];
@@ -322,23 +342,56 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
                 mi++;
             }
         }
+    } else if (want_pack) {
+        MfCompactBlob *h_blob = reinterpret_cast<MfCompactBlob *>(hd + o_blob);
+        MfEnc2Member *h_mem = reinterpret_cast<MfEnc2Member *>(hd + o_mem);
+        for (uint64_t i = 0; i < n; i++) {
+            const uint64_t nm = mf_n_members(src_len[i]);
+            h_blob[i].dst = static_cast<uint8_t *>(d_dst[i]);
+            h_blob[i].dst_cap = dst_cap[i];
+            h_blob[i].first_member = mi;
+            h_blob[i].n_members = (uint32_t)nm;
+            for (uint64_t m = 0; m < nm; m++) {
+                const uint64_t off = m * MF_MEMBER_RAW;
+                const uint64_t rl = std::min<uint64_t>(MF_MEMBER_RAW, src_len[i] - off);
+                MfEnc2Member &M = h_mem[mi];
+                M.src = static_cast<const uint8_t *>(d_src[i]) + off;
+                M.raw_len = (uint32_t)rl;
+                M.n_chunks = (uint32_t)mf_n_chunks(rl);
+                M.first_chunk = ci;
+                ci += M.n_chunks;
+                if (layout == PackContiguous) { M.dst = W.slots.as<uint8_t>() + (size_t)mi * slot_stride; M.dst_cap = slot_stride; M.unit = mi; }
+                else if (layout == PackUnits) { M.dst = static_cast<uint8_t *>(d_dst[i]); M.dst_cap = dst_cap[i]; M.unit = (uint32_t)i; }
+                else {
+                    // a blob whose destination cannot hold all its slots gets no member written at all
+                    const bool room = dst_cap[i] >= (nm - 1) * slot_stride + mf_pack_bound(src_len[i] - (nm - 1) * MF_MEMBER_RAW);
+                    M.dst = static_cast<uint8_t *>(d_dst[i]) + m * slot_stride; M.dst_cap = room ? slot_stride : 0; M.unit = mi;
+                }
+                h_cm[mi] = (uint32_t)i;
+                mi++;
+            }
+        }
     }
     Carver wc;
-    const size_t o_comp = wc.take(sizeof(uint32_t) * n_chunks);
-    const size_t o_hdr = wc.take(sizeof(uint16_t) * n_chunks);
-    const size_t o_seg = wc.take(sizeof(uint16_t) * n_chunks * MF_SEGS_PER_CHUNK);
-    const size_t o_crc = wc.take(sizeof(uint32_t) * n_chunks);
-    const size_t o_cdst = wc.take(sizeof(uint64_t) * n_chunks);
+    const size_t o_comp = wc.take(sizeof(uint32_t) * (v1 ? n_chunks : 0));
+    const size_t o_hdr = wc.take(sizeof(uint16_t) * (v1 ? n_chunks : 0));
+    const size_t o_seg = wc.take(sizeof(uint16_t) * (v1 ? n_chunks : 0) * MF_SEGS_PER_CHUNK);
+    const size_t o_crc = wc.take(sizeof(uint32_t) * (v1 ? n_chunks : 0));
+    const size_t o_cdst = wc.take(sizeof(uint64_t) * (v1 ? n_chunks : 0));
+    const bool compact = want_pack && !v1 && layout == PackContiguous;
+    const size_t o_mlen = wc.take(sizeof(uint64_t) * (compact ? n_members : 0));     // member lengths / status / offsets (compaction)
+    const size_t o_mst = wc.take(sizeof(int32_t) * (compact ? n_members : 0));
+    const size_t o_moff = wc.take(sizeof(uint64_t) * (compact ? n_members : 0));
     const size_t o_ticket = wc.take(sizeof(uint32_t));
     const size_t o_res = wc.take(0);
     Carver rc;
-    W.r_len = rc.take(sizeof(uint64_t) * n, 16);
-    W.r_st = rc.take(sizeof(int32_t) * n, 16);
+    W.r_len = rc.take(sizeof(uint64_t) * n_out, 16);
+    W.r_st = rc.take(sizeof(int32_t) * n_out, 16);
     W.r_sha = rc.take(20 * n, 16);
     W.res_bytes = rc.take(0, 16);
     CU(W.d_work.ensure(o_res + W.res_bytes));
     CU(W.h_res.ensure(W.res_bytes));
-    if (want_pack) CU(W.slots.ensure((size_t)n_chunks * MF_SLOT + 64));
+    if (want_pack && v1) CU(W.slots.ensure((size_t)n_chunks * MF_SLOT + 64));
     uint8_t *dw = W.d_work.as<uint8_t>();
     uint8_t *dd = W.d_desc.as<uint8_t>();
     uint8_t *dres = dw + o_res;
@@ -350,7 +403,8 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         phase = W.phase.as<unsigned long long>();
     }
     CU(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemsetAsync(dres + W.r_st, 0, sizeof(int32_t) * n, s));
+    CU(cudaMemsetAsync(dres + W.r_st, 0, sizeof(int32_t) * n_out, s));
+    if (compact && n_members) CU(cudaMemsetAsync(dw + o_mst, 0, sizeof(int32_t) * n_members, s));
     CU(cudaMemsetAsync(dw + o_ticket, 0, sizeof(uint32_t), s));
     if (upload) {
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
@@ -366,7 +420,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     uint32_t *gate = nullptr;
     const unsigned sha_ctas = (unsigned)((n + MF_SHA_STREAMS_PER_CTA - 1) / MF_SHA_STREAMS_PER_CTA);
     const size_t sha_smem = MF_SHA_UNITS * sizeof(MfShaSmem);
-    if (!upload && !chain && want_pack && sha_ctas <= 32 && wait_value) {
+    if (!upload && !chain && want_pack && sha_ctas <= 64 && wait_value) {
         CU(D.gate.ensure(256));
         gate = D.gate.as<uint32_t>();
         CU(cudaMemsetAsync(gate, 0, sizeof(uint32_t), s));          // before ev_in: both kernels' streams wait on it
@@ -395,33 +449,59 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             D.err = "cuStreamWaitValue32 failed"; return MFCAS_E_CUDA;
         }
         CU(cudaEventRecord(W.ev[2], sc));
-        if (n_chunks) {
-            unsigned sha_sms = 0;             // SMs owned by SHA-1 CTAs of this wave and of the waves still in flight
-            for (WaveCtx &O : D.ring) if (&O == &W || O.state == 1) sha_sms += O.sha_ctas;
-            const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, MF_SM_SLOTS - 2u * std::min(sha_sms, 148u));
-            mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_groups, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
-                reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
-                W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
-                reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket),
-                reinterpret_cast<const uint32_t *>(dd + o_grp), n_groups);
-            CU(cudaGetLastError());
-            D.launches++;
-        }
-        CU(cudaEventRecord(W.ev[3], sc));
-        mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, sc>>>(
-            reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
-            reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint16_t *>(dw + o_hdr),
-            reinterpret_cast<const uint16_t *>(dw + o_seg), reinterpret_cast<const uint32_t *>(dw + o_crc),
-            reinterpret_cast<uint64_t *>(dw + o_cdst), reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
-        CU(cudaGetLastError());
-        D.launches++;
-        if (n_chunks) {
-            mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, sc>>>(
+        unsigned sha_sms = 0;             // SMs owned by SHA-1 CTAs of this wave and of the waves still in flight
+        for (WaveCtx &O : D.ring) if (&O == &W || O.state == 1) sha_sms += O.sha_ctas;
+        if (v1) {
+            if (n_chunks) {
+                const unsigned enc_cap = std::max(MF_ENC_GRID_MIN, MF_SM_SLOTS - 2u * std::min(sha_sms, 148u));
+                mf_deflate_kernel<<<(unsigned)std::min<uint64_t>(n_groups, enc_cap), MF_ENC_THREADS, sizeof(MfEncSmem), sc>>>(
+                    reinterpret_cast<const MfEncMember *>(dd + o_mem), reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks,
+                    W.slots.as<uint8_t>(), reinterpret_cast<uint32_t *>(dw + o_comp), reinterpret_cast<uint16_t *>(dw + o_hdr),
+                    reinterpret_cast<uint16_t *>(dw + o_seg), reinterpret_cast<uint32_t *>(dw + o_crc), flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket),
+                    reinterpret_cast<const uint32_t *>(dd + o_grp), n_groups);
+                CU(cudaGetLastError());
+                D.launches++;
+            }
+            CU(cudaEventRecord(W.ev[3], sc));
+            mf_gather_layout_kernel<<<(unsigned)n, MF_GA_THREADS, 0, sc>>>(
                 reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
-                reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, W.slots.as<uint8_t>(),
-                reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint64_t *>(dw + o_cdst));
+                reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint16_t *>(dw + o_hdr),
+                reinterpret_cast<const uint16_t *>(dw + o_seg), reinterpret_cast<const uint32_t *>(dw + o_crc),
+                reinterpret_cast<uint64_t *>(dw + o_cdst), reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
             CU(cudaGetLastError());
             D.launches++;
+            if (n_chunks) {
+                mf_gather_copy_kernel<<<(unsigned)n_chunks, 256, 0, sc>>>(
+                    reinterpret_cast<const MfEncBlob *>(dd + o_blob), reinterpret_cast<const MfEncMember *>(dd + o_mem),
+                    reinterpret_cast<const uint32_t *>(dd + o_cm), (uint32_t)n_chunks, W.slots.as<uint8_t>(),
+                    reinterpret_cast<const uint32_t *>(dw + o_comp), reinterpret_cast<const uint64_t *>(dw + o_cdst));
+                CU(cudaGetLastError());
+                D.launches++;
+            }
+        } else {
+            // the member-owned encoder: one CTA per SM on the SMs the hash CTAs in flight leave free
+            const unsigned enc_cap = std::max(74u, 148u - std::min(sha_sms, 148u));
+            uint64_t *mlen = compact ? reinterpret_cast<uint64_t *>(dw + o_mlen) : reinterpret_cast<uint64_t *>(dres + W.r_len);
+            int32_t *mst = compact ? reinterpret_cast<int32_t *>(dw + o_mst) : reinterpret_cast<int32_t *>(dres + W.r_st);
+            if (n_members) {
+                mf_deflate2_kernel<<<(unsigned)std::min<uint64_t>(n_members, enc_cap), MF2_THREADS, sizeof(MfEnc2Smem), sc>>>(
+                    reinterpret_cast<const MfEnc2Member *>(dd + o_mem), (uint32_t)n_members, mlen, mst, flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket));
+                CU(cudaGetLastError());
+                D.launches++;
+            }
+            CU(cudaEventRecord(W.ev[3], sc));
+            if (compact && n) {
+                mf_compact_layout_kernel<<<(unsigned)n, 256, 0, sc>>>(reinterpret_cast<const MfCompactBlob *>(dd + o_blob), mlen, mst,
+                                                                      reinterpret_cast<uint64_t *>(dw + o_moff), reinterpret_cast<uint64_t *>(dres + W.r_len),
+                                                                      reinterpret_cast<int32_t *>(dres + W.r_st));
+                CU(cudaGetLastError());
+                const unsigned tiles = (unsigned)((slot_stride + MF_COMPACT_TILE - 1) / MF_COMPACT_TILE);
+                mf_compact_copy_kernel<<<(unsigned)(n_members * tiles), 256, 0, sc>>>(
+                    reinterpret_cast<const MfCompactBlob *>(dd + o_blob), reinterpret_cast<const uint32_t *>(dd + o_cm), W.slots.as<uint8_t>(), slot_stride,
+                    mlen, reinterpret_cast<const uint64_t *>(dw + o_moff), reinterpret_cast<const int32_t *>(dres + W.r_st), tiles);
+                CU(cudaGetLastError());
+                D.launches += 2;
+            }
         }
         CU(cudaEventRecord(W.ev[4], sc));
         CU(cudaEventRecord(W.ev_cmp, sc));
@@ -433,7 +513,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     CU(cudaEventRecord(W.ev_res, s));
     CU(cudaMemcpyAsync(W.h_res.as<uint8_t>() + W.r_sha, dres + W.r_sha, W.res_bytes - W.r_sha, cudaMemcpyDeviceToHost, s2));
     CU(cudaEventRecord(W.ev_shares, s2));
-    W.n = n; W.n_chunks = n_chunks; W.sha_ctas = sha_ctas; W.timed_pack = want_pack;
+    W.n = n; W.n_out = n_out; W.n_chunks = n_chunks; W.sha_ctas = sha_ctas; W.timed_pack = want_pack;
     return MFCAS_OK;
 }
 
@@ -444,8 +524,8 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
     const uint64_t n = W.n;
     if (sha1) memcpy(sha1, hr + W.r_sha, 20 * n);
     if (W.timed_pack) {
-        memcpy(dst_len, hr + W.r_len, sizeof(uint64_t) * n);
-        memcpy(status, hr + W.r_st, sizeof(int32_t) * n);
+        memcpy(dst_len, hr + W.r_len, sizeof(uint64_t) * W.n_out);
+        memcpy(status, hr + W.r_st, sizeof(int32_t) * W.n_out);
         cudaEventElapsedTime(&D.ms[1], W.ev[2], W.ev[3]);
         cudaEventElapsedTime(&D.ms[2], W.ev[3], W.ev[4]);
     } else if (status) {
@@ -466,6 +546,22 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
             const uint64_t nc = W.n_chunks;
             std::vector<unsigned long long> h(nc * 16);
             CU(cudaMemcpy(h.data(), W.phase.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            if (!enc_v1()) {
+                // member-owned encoder: clock64 of thread 0 at 0 start, 1 chunk loaded, 2 LZ done (warp 0), 3 sweep done,
+                // 4 verdict known, 5 codes settled (rebuilt if rejected), 6 image complete, 7 stored
+                static const char *nm2[7] = {"wait_load", "lz77(w0)", "sweep(w0)", "verdict", "rebuild", "place", "store"};
+                double acc[7] = {0};
+                uint64_t rebuilt = 0;
+                for (uint64_t c = 0; c < nc; c++) {
+                    for (int k = 0; k < 7; k++) acc[k] += (double)(h[c * 16 + k + 1] - h[c * 16 + k]);
+                    if (h[c * 16 + 5] - h[c * 16 + 4] > 2000) rebuilt++;
+                }
+                fprintf(stderr, "[mfcas phase] deflate2, mean cycles per chunk over %llu chunks:", (unsigned long long)nc);
+                double tot = 0;
+                for (int k = 0; k < 7; k++) { fprintf(stderr, " %s=%.0f", nm2[k], acc[k] / (double)nc); tot += acc[k]; }
+                fprintf(stderr, " total=%.0f | chunks with rebuilt codes: %llu\n", tot / (double)nc, (unsigned long long)rebuilt);
+                return MFCAS_OK;
+            }
             // boundaries in program order: 0 start,1 loaded,2 crc,3 lz,8 litlen code,9 dist code,10 rle,11 zeroed,12 cl code,13 header,4,5,6,7
             static const int seq[14] = {0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 4, 5, 6, 7};
             static const char *nm[13] = {"load", "crc", "lz77", "codes(warp0)", "codes_sync", "hdr_scan", "hdr_tokens", "hdr_clcode", "hdr_write", "sync", "bitcount", "pack", "store"};
@@ -816,7 +912,7 @@ int run_shard_extents(mfcas_ctx *ctx, DeviceState &D, const ExtIO &io) {
                 if (std::find(seen.begin(), seen.end(), lw) == seen.end()) { seen.push_back(lw); deps.push_back(D.ring[lw % D.ring.size()].ev_sha); }
             }
         }
-        rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), true, &up, chain.data(), &deps);
+        rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), true, &up, chain.data(), &deps, PackUnits);
         if (rc != MFCAS_OK) break;
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));
         {
@@ -1008,6 +1104,71 @@ int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *cons
     if (rc == MFCAS_OK) rc = pack_collect(D, W, dst_len, sha1, status);
     if (rc != MFCAS_OK) ctx->err = D.err;
     return rc;
+}
+
+int mfcas_pack_device_extents(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *const *d_src, const uint64_t *src_len,
+                              void *const *d_dst, const uint64_t *dst_cap, uint64_t *ext_off, uint64_t *ext_len, uint8_t *sha1, int32_t *status) {
+    if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return MFCAS_E_ARG;
+    if (n && (!d_src || !src_len || !d_dst || !dst_cap || !ext_off || !ext_len || !sha1 || !status)) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &D = ctx->devs[(size_t)dev_slot];
+    if (n == 0) return MFCAS_OK;
+    cudaSetDevice(D.dev);
+    WaveCtx &W = D.ring[0];
+    uint64_t n_members = 0;
+    for (uint64_t i = 0; i < n; i++) n_members += ext_count(src_len[i]);
+    std::vector<uint64_t> mlen(n_members);
+    std::vector<int32_t> mst(n_members);
+    int rc = pack_submit(D, W, ctx->flags, n, d_src, src_len, d_dst, dst_cap, true, nullptr, nullptr, nullptr, PackSlots);
+    if (rc == MFCAS_OK) rc = pack_collect(D, W, mlen.data(), sha1, mst.data());
+    if (rc != MFCAS_OK) { ctx->err = D.err; return rc; }
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        status[i] = 0;
+        const uint64_t c = ext_count(src_len[i]);
+        for (uint64_t m = 0; m < c; m++, k++) {
+            ext_off[k] = m * ext_slot();
+            ext_len[k] = mst[k] ? 0 : mlen[k];
+            if (mst[k] && !status[i]) status[i] = mst[k];
+        }
+    }
+    return MFCAS_OK;
+}
+
+int mfcas_compact_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, void *const *d_dst, const uint64_t *src_len, const uint64_t *ext_len,
+                         uint64_t *dst_len) {
+    if (!ctx || dev_slot < 0 || (size_t)dev_slot >= ctx->devs.size()) return MFCAS_E_ARG;
+    if (n && (!d_dst || !src_len || !ext_len || !dst_len)) return MFCAS_E_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &D = ctx->devs[(size_t)dev_slot];
+    if (n == 0) return MFCAS_OK;
+    CU(cudaSetDevice(D.dev));
+    WaveCtx &W = D.ring[0];
+    std::vector<uint64_t> base(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) base[i + 1] = base[i] + ext_count(src_len[i]);
+    const uint64_t nm = base[n];
+    Carver hc;
+    const size_t o_dst = hc.take(sizeof(void *) * n);
+    const size_t o_base = hc.take(sizeof(uint64_t) * (n + 1));
+    const size_t o_len = hc.take(sizeof(uint64_t) * nm);
+    const size_t o_out = hc.take(sizeof(uint64_t) * n);
+    const size_t bytes = hc.take(0);
+    CU(W.h_desc.ensure(bytes));
+    CU(W.d_desc.ensure(bytes));
+    uint8_t *hd = W.h_desc.as<uint8_t>(), *dd = W.d_desc.as<uint8_t>();
+    memcpy(hd + o_dst, d_dst, sizeof(void *) * n);
+    memcpy(hd + o_base, base.data(), sizeof(uint64_t) * (n + 1));
+    memcpy(hd + o_len, ext_len, sizeof(uint64_t) * nm);
+    cudaStream_t s = W.stream;
+    CU(cudaMemcpyAsync(dd, hd, o_out, cudaMemcpyHostToDevice, s));
+    mf_compact_inplace_kernel<<<(unsigned)n, 1024, 0, s>>>(reinterpret_cast<uint8_t *const *>(dd + o_dst), reinterpret_cast<const uint64_t *>(dd + o_base),
+                                                           reinterpret_cast<const uint64_t *>(dd + o_len), ext_slot(), reinterpret_cast<uint64_t *>(dd + o_out));
+    CU(cudaGetLastError());
+    D.launches++;
+    CU(cudaMemcpyAsync(hd + o_out, dd + o_out, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    memcpy(dst_len, hd + o_out, sizeof(uint64_t) * n);
+    return MFCAS_OK;
 }
 
 int mfcas_unpack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n, const void *const *d_src, const uint64_t *src_len,

@@ -32,7 +32,8 @@ def test_pack_bound_matches_format_constants():
     assert lib.mfcas_pack_bound(1) == 45 + 72 + 5 + 1
     n = 16777379                                   # pickle of a 16 MiB fp32 array
     chunks = -(-n // 32768)
-    assert lib.mfcas_pack_bound(n) == 45 + chunks * 77 + n
+    members = -(-n // (64 * 32768))                # a member is one 2 MiB stripe (64 chunks)
+    assert lib.mfcas_pack_bound(n) == members * 45 + chunks * 77 + n
     assert lib.mfcas_pack_bound(n) == model_lib.lib().model_pack_bound(n)
 
 

@@ -300,7 +300,9 @@ def test_c4_nested_256x256_join_loads(gpu_codec, shm_dir):
     for o in range(outer):
         t0 = time.perf_counter()
         l0 = gpu_codec.counters()["kernel_launches"]
-        dss = TaskDataStoreSet(fds, "1", pathspecs=["1/leaf/%d_%d" % (o, j) for j in range(inner)], prefetch_data_artifacts=["x"])
+        # (the control artifact goes into the prefetch as in the reference's join, task.py:252-279: the set indexes its
+        # datastores by pathspec_index, which reads every input's _foreach_stack)
+        dss = TaskDataStoreSet(fds, "1", pathspecs=["1/leaf/%d_%d" % (o, j) for j in range(inner)], prefetch_data_artifacts=["x", "_foreach_stack"])
         l1 = gpu_codec.counters()["kernel_launches"]
         got = [ds["x"] for ds in dss]                             # served from the prefetch cache, pathspec order
         assert gpu_codec.counters()["kernel_launches"] == l1
@@ -328,20 +330,21 @@ def test_c4_nested_256x256_join_loads(gpu_codec, shm_dir):
 def test_c4_join_loads_reference_written_inputs(gpu_codec, shm_dir):
     """The C4 load side on blobs written by the reference's code path (zlib level 3, one stream, no index): one inner
     join's 256 inputs of 1 MiB through TaskDataStoreSet, one batched unpack."""
-    from concurrent.futures import ProcessPoolExecutor
     from metaflow_b200 import FlowDataStore, LocalStorage, TaskDataStoreSet
+    from metaflow_b200.tuple_util import ForeachFrame
     inner, elems = 256, 262144
     rng = np.random.default_rng(45)
     arrays = [rng.standard_normal(elems, dtype=np.float32) for _ in range(inner)]
     fds = FlowDataStore("C4Ref", storage_impl=LocalStorage, ds_root=shm_dir, codec=gpu_codec)
     for j, a in enumerate(arrays):
-        objects, info = ref_path.save_artifacts(shm_dir, "C4Ref", [("x", a)])      # the reference's writer, restated
+        stack = [ForeachFrame("fan", "inner", inner, j, j)]
+        objects, info = ref_path.save_artifacts(shm_dir, "C4Ref", [("x", a), ("_foreach_stack", stack)])      # the reference's writer, restated
         w = fds.get_task_datastore("1", "leaf", str(j), attempt=0, mode="w")
         w.init_task()
         w._objects.update(objects); w._info.update(info)
         w.done()
     t0 = time.perf_counter()
-    dss = TaskDataStoreSet(fds, "1", pathspecs=["1/leaf/%d" % j for j in range(inner)], prefetch_data_artifacts=["x"])
+    dss = TaskDataStoreSet(fds, "1", pathspecs=["1/leaf/%d" % j for j in range(inner)], prefetch_data_artifacts=["x", "_foreach_stack"])
     got = [ds["x"] for ds in dss]
     dt = time.perf_counter() - t0
     fds.ca_store.set_blob_cache(None)
