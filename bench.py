@@ -394,6 +394,8 @@ def run_ours(args, rank, world, local_rank):
     assert esha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
     assert gzip.decompress(h_pk[:eplen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"
     barrier()
+    ec0 = [u64(0), u64(0), u64(0)]
+    lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in ec0])
     for s in range(e2e_steps):
         generate(30_000 + s)
         for part in range(n // ne):
@@ -404,8 +406,9 @@ def run_ours(args, rank, world, local_rank):
             barrier()
             b = load_host()
             e2e_save += a; e2e_load += b
-            pb = sum(eplen)
-            h2d += ne * blob_len + pb; d2h += ne * ecap + ne * blob_len
+    ec1 = [u64(0), u64(0), u64(0)]
+    lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in ec1])
+    h2d, d2h = ec1[1].value - ec0[1].value, ec1[2].value - ec0[2].value         # bytes the library really moved each way
     assert h_out[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes() == h_in[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes()
 
     # ---- L-api: objects -> TaskDataStore.save_artifacts -> files on tmpfs -> load_artifacts -> objects,

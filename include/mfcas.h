@@ -59,6 +59,11 @@ void mfcas_destroy(mfcas_ctx *ctx);
 /* Last error text of this context (valid until the next call on the context). */
 const char *mfcas_last_error(mfcas_ctx *ctx);
 
+/* Moves the CALLING THREAD next to CUDA device `device`: CPU affinity restricted to the cores of the device's NUMA
+ * node, memory policy "prefer that node" (so page-locked buffers allocated afterwards are local to the GPU's PCIe
+ * root).  mfcas_create does this itself for a one-device context unless MFCAS_NUMA=0.  Returns the node, -1 if unknown. */
+int mfcas_bind_thread_to_device(int device);
+
 /* Page-locked host memory for zero-staging transfers. */
 void *mfcas_alloc_pinned(uint64_t bytes);
 void mfcas_free_pinned(void *p);

@@ -36,6 +36,7 @@ SIGNATURES = [
     ("mfcas_create", ctypes.c_void_p, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint64, ctypes.c_uint32]),
     ("mfcas_destroy", None, [ctypes.c_void_p]),
     ("mfcas_last_error", ctypes.c_char_p, [ctypes.c_void_p]),
+    ("mfcas_bind_thread_to_device", ctypes.c_int, [ctypes.c_int]),
     ("mfcas_alloc_pinned", ctypes.c_void_p, [ctypes.c_uint64]),
     ("mfcas_free_pinned", None, [ctypes.c_void_p]),
     ("mfcas_pack_bound", ctypes.c_uint64, [ctypes.c_uint64]),

@@ -44,7 +44,13 @@ struct MfEnc2Member {
 #define MF2_STAGE_WORDS (32u * MF2_ROW)      // 2176 bytes per warp: the LZ hash table (2 KiB) first, the staged bits afterwards
 #define MF2_LL_MAXBITS 14
 #define MF2_IMG_BYTES (MF_CHUNK + 64u)
-#define MF2_HIST_STEP 4                       // every 4th literal position is sampled, weight 4
+#define MF2_ACCEPT_TOL 128.f                  // codes are kept while they cost at most 1/128 more than fresh ones could
+#define MF2_HIST_STEP 4                       // 8 of a lane's 32 byte positions are sampled, weight 4
+// The sampled positions must not alias with the element size of the data (a stride of 4 over float32 data sees one
+// byte lane of every element only -- the uniformly distributed low mantissa byte): both sets hold every residue mod 8
+// exactly once (so every residue mod 4 twice), and segments alternate between them.
+#define MF2_SAMPLE_A ((1u << 0) | (1u << 5) | (1u << 10) | (1u << 15) | (1u << 17) | (1u << 22) | (1u << 27) | (1u << 28))
+#define MF2_SAMPLE_B ((1u << 2) | (1u << 7) | (1u << 8) | (1u << 13) | (1u << 19) | (1u << 20) | (1u << 25) | (1u << 30))
 
 // 5-bit sliced CRC tables (conflict-free in shared memory): g_mf_crc5[j][v] = raw CRC state after the 32-bit word
 // (v << 5j) followed by nothing, i.e. the slice-by-4 step applied to that word; g_mf_crcM[j][v] = (v << 5j) * x^(8*32768)
@@ -90,7 +96,8 @@ struct __align__(16) MfEnc2Smem {
     uint4 carry;                                    // bytes of the last, partial 16-byte vector of the previous chunk
     unsigned long long mbar[2];
     uint32_t crc_part[MF2_WARPS];
-    uint32_t ticket, accept, stored, comp_bytes, total_bits, crc_tail;
+    uint32_t ticket, total_bits, crc_tail;
+    uint32_t dec_cost, dec_miss, dec_a_ll, dec_b_ll, dec_a_d, dec_b_d;     // this chunk against the codes in use
 };
 
 static_assert(sizeof(MfEnc2Smem) <= 227u * 1024u, "MfEnc2Smem must fit the 227 KB of shared memory a CTA can have");
@@ -120,7 +127,7 @@ struct Mf2Stage {
 
 // One lane's 32-byte span of a segment: literal histogram sample, token packing into the staging row.
 // Returns the number of bits staged (0 when !PACK).  wd[] = the span's bytes.
-template <bool PACK, bool HIST>
+template <bool PACK, bool HIST, uint32_t SAMPLE>
 __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)[8], uint32_t lo, uint32_t hi, const uint32_t *matches,
                                              uint32_t nmatch, uint32_t lane, uint32_t *row) {
     if (lo >= hi) { if (PACK) row[0] = 0; return 0; }
@@ -137,7 +144,8 @@ __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
             const uint32_t b0 = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu, b1 = (wd[k >> 2] >> (((k + 1) & 3) * 8)) & 0xFFu;
-            if (HIST && (k % MF2_HIST_STEP) == 0) atomicAdd(&S.ll_hist[b0], (uint32_t)MF2_HIST_STEP);
+            if (HIST && ((SAMPLE >> k) & 1u)) atomicAdd(&S.ll_hist[b0], (uint32_t)MF2_HIST_STEP);
+            if (HIST && ((SAMPLE >> (k + 1)) & 1u)) atomicAdd(&S.ll_hist[b1], (uint32_t)MF2_HIST_STEP);
             if (PACK) {
                 const uint32_t e0 = lit[b0 * 8u], e1 = lit[b1 * 8u];
                 const uint32_t l0 = e0 >> 16, l1 = e1 >> 16;
@@ -164,7 +172,7 @@ __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)
                 next_pos = mi < nmatch ? mf_match_pos(matches[mi]) : 0xFFFFFFFFu;
             } else {
                 const uint32_t byte = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
-                if (HIST && (k % MF2_HIST_STEP) == 0) atomicAdd(&S.ll_hist[byte], (uint32_t)MF2_HIST_STEP);
+                if (HIST && ((SAMPLE >> k) & 1u)) atomicAdd(&S.ll_hist[byte], (uint32_t)MF2_HIST_STEP);
                 if (PACK) { const uint32_t e = lit[byte * 8u]; w.put(e & 0xFFFFu, e >> 16); }
                 p++;
             }
@@ -299,6 +307,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             if (!last && tid == 0) issue_load(ci + 1);           // buffer b^1 was last read two barriers ago
             for (uint32_t i = tid; i < 288; i += MF2_THREADS) S.ll_hist[i] = 0;
             if (tid < 32) S.d_hist[tid] = 0;
+            if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }
             if (b == 0) { mf_mbar_wait(&S.mbar[0], par0); par0 ^= 1u; } else { mf_mbar_wait(&S.mbar[1], par1); par1 ^= 1u; }
             uint8_t *data = S.data[b];
             if (len < MF_CHUNK) {                                 // bytes past the end: nothing downstream may depend on stale ones
@@ -347,8 +356,14 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             uint32_t bits = 0;
             const bool have_codes = S.cache_hdr_bits != 0;
             if (seglen) {
-                if (have_codes) bits = mf2_span<true, true>(S, wd, lo, hi, S.match[seg], nm, lane, S.stage[warp] + lane * MF2_ROW);
-                else mf2_span<false, true>(S, wd, lo, hi, S.match[seg], nm, lane, nullptr);
+                uint32_t *row = S.stage[warp] + lane * MF2_ROW;
+                if (seg & 1u) {
+                    if (have_codes) bits = mf2_span<true, true, MF2_SAMPLE_B>(S, wd, lo, hi, S.match[seg], nm, lane, row);
+                    else mf2_span<false, true, MF2_SAMPLE_B>(S, wd, lo, hi, S.match[seg], nm, lane, nullptr);
+                } else {
+                    if (have_codes) bits = mf2_span<true, true, MF2_SAMPLE_A>(S, wd, lo, hi, S.match[seg], nm, lane, row);
+                    else mf2_span<false, true, MF2_SAMPLE_A>(S, wd, lo, hi, S.match[seg], nm, lane, nullptr);
+                }
             }
             uint32_t incl = mf_warp_incl_scan(bits, lane);
             uint32_t lane_off = incl - bits;
@@ -362,36 +377,41 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 uint4 *z = reinterpret_cast<uint4 *>(S.img);
                 for (uint32_t i = tid; i < MF2_IMG_BYTES / 16; i += MF2_THREADS) z[i] = (i == 0) ? S.carry : make_uint4(0, 0, 0, 0);
             }
-            // ---- warp 0: price the codes in use against this chunk's (sampled) statistics
-            if (warp == 0) {
-                uint32_t cost = 0, a_ll = 0, b_ll = 0, a_d = 0, b_d = 0, miss = 0;
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    const uint32_t s = (uint32_t)k * 32u + lane;
-                    const uint32_t h = s < 286u ? S.ll_hist[s] : 0u, l = s < 286u ? S.ll_lens[s] : 0u;
-                    miss |= (h != 0 && l == 0);
-                    cost += h * l; a_ll += h;
-                    b_ll += h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u;
+            // ---- price the codes in use against this chunk's (sampled) statistics: symbols 0..285 on warps 0..8, distance
+            // symbols on warp 9 (integer sums: the verdict must not depend on the order of the atomics); warp 10 meanwhile
+            // scans the segment lengths as if the codes are kept
+            if (warp < 10) {
+                uint32_t h = 0, l = 0;
+                if (warp < 9) { if (tid < 286) { h = S.ll_hist[tid]; l = S.ll_lens[tid]; } }
+                else if (lane < 30u) { h = S.d_hist[lane]; l = S.d_lens[lane]; }
+                const uint32_t miss = __ballot_sync(0xFFFFFFFFu, h != 0 && l == 0);
+                const uint32_t cost = mf_warp_sum(h * l), a = mf_warp_sum(h);
+                const uint32_t bb = mf_warp_sum(h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u);
+                if (lane == 0) {
+                    atomicAdd(&S.dec_cost, cost);
+                    if (miss) atomicOr(&S.dec_miss, 1u);
+                    if (warp < 9) { atomicAdd(&S.dec_a_ll, a); atomicAdd(&S.dec_b_ll, bb); }
+                    else { atomicAdd(&S.dec_a_d, a); atomicAdd(&S.dec_b_d, bb); }
                 }
-                {
-                    const uint32_t h = lane < 30u ? S.d_hist[lane] : 0u, l = lane < 30u ? S.d_lens[lane] : 0u;
-                    miss |= (h != 0 && l == 0);
-                    cost += h * l; a_d += h;
-                    b_d += h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u;
-                }
-                cost = mf_warp_sum(cost); a_ll = mf_warp_sum(a_ll); b_ll = mf_warp_sum(b_ll); a_d = mf_warp_sum(a_d); b_d = mf_warp_sum(b_d);
-                miss = __any_sync(0xFFFFFFFFu, miss != 0);
-                float e16 = 0.f;
-                if (a_ll > 1) e16 += (float)a_ll * __log2f((float)a_ll) * 16.f - (float)b_ll;
-                if (a_d > 1) e16 += (float)a_d * __log2f((float)a_d) * 16.f - (float)b_d;
-                e16 = fmaxf(e16, 0.f);
-                const float nsym = (float)(a_ll + a_d);
-                const bool ok = have_codes && !miss && (float)cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / 128.f) + 1024.f;
-                if (lane == 0) S.accept = ok ? 1u : 0u;
+            } else if (warp == 10) {
+                const uint32_t sb = S.seg_bits[lane];
+                const uint32_t sc = mf_warp_incl_scan(sb, lane);
+                S.seg_off[lane] = S.cache_hdr_bits + sc - sb;
+                if (lane == 31) S.total_bits = S.cache_hdr_bits + sc;
             }
-            __syncthreads();                                     // ---- barrier 2: verdict
+            __syncthreads();                                     // ---- barrier 2: sums, offsets
             MF2_PHASE(4);
-            if (!S.accept) {
+            bool accept;
+            {
+                float e16 = 0.f;
+                { const uint32_t a = S.dec_a_ll, bsum = S.dec_b_ll; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
+                { const uint32_t a = S.dec_a_d, bsum = S.dec_b_d; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
+                e16 = fmaxf(e16, 0.f);
+                const float nsym = (float)(S.dec_a_ll + S.dec_a_d);
+                accept = have_codes && S.dec_miss == 0 &&
+                         (float)S.dec_cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / MF2_ACCEPT_TOL) + 1024.f;
+            }
+            if (!accept) {
                 // ---- fresh codes from this chunk's statistics (every literal keeps a code: floor count 1), then pack again
                 if (tid < 256 && S.ll_hist[tid] == 0) S.ll_hist[tid] = 1;
                 if (tid < MF_HDR_CACHE_WORDS) S.hdr_cache[tid] = 0;
@@ -417,37 +437,37 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 for (uint32_t i = tid; i < 256u * 8u; i += MF2_THREADS) S.lit_codes[i] = S.ll_codes[i >> 3];
                 __syncthreads();
                 bits = 0;
-                if (seglen) bits = mf2_span<true, false>(S, wd, lo, hi, S.match[seg], nm, lane, S.stage[warp] + lane * MF2_ROW);
+                if (seglen) bits = mf2_span<true, false, 0u>(S, wd, lo, hi, S.match[seg], nm, lane, S.stage[warp] + lane * MF2_ROW);
                 incl = mf_warp_incl_scan(bits, lane);
                 lane_off = incl - bits;
                 if (lane == 31) S.seg_bits[seg] = incl;
                 __syncthreads();
+                if (warp == 10) {
+                    const uint32_t sb = S.seg_bits[lane];
+                    const uint32_t sc = mf_warp_incl_scan(sb, lane);
+                    S.seg_off[lane] = S.cache_hdr_bits + sc - sb;
+                    if (lane == 31) S.total_bits = S.cache_hdr_bits + sc;
+                }
+                __syncthreads();
             }
             MF2_PHASE(5);
-            // ---- warp 0: segment offsets, chunk size, stored-or-not, index entry
+            // ---- chunk size, stored-or-not (every thread computes the same), index entry
             const uint32_t hdr_bits = S.cache_hdr_bits;
-            if (warp == 0) {
-                const uint32_t sb = S.seg_bits[lane];
-                const uint32_t sc = mf_warp_incl_scan(sb, lane);
-                S.seg_off[lane] = hdr_bits + sc - sb;
-                const uint32_t tokens = __shfl_sync(0xFFFFFFFFu, sc, 31);
+            bool stored;
+            uint32_t comp_bytes;
+            {
                 const uint32_t eob = S.ll_codes[256];
-                const uint32_t end_tokens = hdr_bits + tokens;
-                const uint32_t end_bits = end_tokens + (eob >> 16) + 3u;          // + empty stored block header (000)
-                const uint32_t dyn_bytes = ((end_bits + 7u) >> 3) + 4u;           // + LEN/NLEN of the sync marker
-                const bool stored = dyn_bytes >= len + 5u;
-                if (lane == 0) {
-                    S.total_bits = end_tokens;
-                    S.stored = stored ? 1u : 0u;
-                    S.comp_bytes = stored ? len + 5u : dyn_bytes;
-                    S.idx_chunk[ci][0] = stored ? len + 5u : dyn_bytes;
-                    S.idx_chunk[ci][1] = stored ? (uint32_t)MF_STORED_MARK : hdr_bits;
-                }
-                S.idx_seg[ci][lane] = stored ? (uint16_t)0 : (uint16_t)sb;
+                const uint32_t end_bits = S.total_bits + (eob >> 16) + 3u;          // + empty stored block header (000)
+                const uint32_t dyn_bytes = ((end_bits + 7u) >> 3) + 4u;             // + LEN/NLEN of the sync marker
+                stored = dyn_bytes >= len + 5u;
+                comp_bytes = stored ? len + 5u : dyn_bytes;
             }
-            __syncthreads();                                     // ---- barrier 3: offsets, verdicts
+            if (warp == 11) {
+                if (lane == 0) { S.idx_chunk[ci][0] = comp_bytes; S.idx_chunk[ci][1] = stored ? (uint32_t)MF_STORED_MARK : hdr_bits; }
+                S.idx_seg[ci][lane] = stored ? (uint16_t)0 : (uint16_t)S.seg_bits[lane];
+            }
             const uint32_t cbits = 8u * (uint32_t)(woff & 15u);   // the chunk starts behind the carried bytes
-            if (!S.stored) {
+            if (!stored) {
                 // every lane shifts its staged bits to their place: only its first and last word are shared
                 if (bits) {
                     const uint32_t d0 = cbits + S.seg_off[seg] + lane_off;
@@ -484,30 +504,50 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                     atomicOr(&S.img[(byte + 1) >> 2], 0xFFu << (((byte + 1) & 3u) * 8u));
                 }
             } else {
-                // stored block: 00 | LEN | NLEN | raw bytes, behind the carried bytes (any alignment: byte stores)
-                uint8_t *ib = reinterpret_cast<uint8_t *>(S.img) + (cbits >> 3);
-                for (uint32_t j = tid; j < len + 5u; j += MF2_THREADS) {
-                    uint8_t v;
-                    if (j == 0) v = 0;
-                    else if (j == 1) v = (uint8_t)len;
-                    else if (j == 2) v = (uint8_t)(len >> 8);
-                    else if (j == 3) v = (uint8_t)~len;
-                    else if (j == 4) v = (uint8_t)((~len) >> 8);
-                    else v = data[j - 5u];
-                    ib[j] = v;
+                // stored block: 00 | LEN | NLEN | raw bytes behind the carried bytes.  Every lane still holds its 32 raw
+                // bytes in registers: they go to their (byte-shifted) place like staged bits do.
+                const uint32_t g0 = base + lo;
+                const uint32_t nby = g0 < len ? min(32u, len - g0) : 0u;
+                if (nby) {
+                    const uint32_t d0 = cbits + 40u + 8u * g0, nbits = 8u * nby;
+                    const uint32_t sh = d0 & 31u, wb = d0 >> 5;
+                    uint32_t prev = 0;
+#pragma unroll
+                    for (int k = 0; k <= 8; k++) {
+                        uint32_t cur = 0;
+                        if (k < 8) {
+                            const uint32_t vb = nby > 4u * (uint32_t)k ? min(4u, nby - 4u * (uint32_t)k) : 0u;
+                            cur = vb >= 4u ? wd[k < 8 ? k : 0] : (wd[k < 8 ? k : 0] & ((1u << (8u * vb)) - 1u));
+                        }
+                        if (32u * (uint32_t)k < nbits + sh) {
+                            const uint32_t v = __funnelshift_l(prev, cur, sh);
+                            const bool whole = k > 0 && 32u * ((uint32_t)k + 1u) <= nbits + sh;
+                            if (whole) S.img[wb + k] = v; else atomicOr(&S.img[wb + k], v);
+                        }
+                        prev = cur;
+                    }
+                }
+                if (tid == 64) {
+                    uint8_t *ib = reinterpret_cast<uint8_t *>(S.img) + (cbits >> 3);    // nobody else touches these 5 bytes' words' other bytes concurrently except by atomicOr
+                    const uint32_t hb[5] = {0u, len & 0xFFu, (len >> 8) & 0xFFu, (~len) & 0xFFu, ((~len) >> 8) & 0xFFu};
+                    for (uint32_t j = 0; j < 5; j++) {
+                        const uint32_t at = (cbits >> 3) + j;
+                        atomicOr(&S.img[at >> 2], hb[j] << (8u * (at & 3u)));
+                    }
+                    (void)ib;
                 }
             }
             MF2_PHASE(6);
             __syncthreads();                                     // ---- barrier 4: image complete
             {
-                const uint32_t total = (uint32_t)(woff & 15u) + S.comp_bytes;
+                const uint32_t total = (uint32_t)(woff & 15u) + comp_bytes;
                 const uint32_t nv = total >> 4;
                 uint4 *g = reinterpret_cast<uint4 *>(mem.dst + (woff & ~15ull));
                 const uint4 *s = reinterpret_cast<const uint4 *>(S.img);
                 for (uint32_t i = tid; i < nv; i += MF2_THREADS) g[i] = s[i];
                 if (tid == (nv & (MF2_THREADS - 1u))) S.carry = s[nv];               // the partial last vector goes with the next chunk
             }
-            woff += S.comp_bytes;
+            woff += comp_bytes;
             MF2_PHASE(7);
             __syncthreads();                                     // ---- barrier 5: shared memory is reused by the next chunk
 #undef MF2_PHASE

@@ -12,6 +12,7 @@
 #include <vector>
 #include "../../metaflow_b200/csrc/mf_core.h"
 #include "../../metaflow_b200/csrc/mf_inflate_core.h"
+#include "../../metaflow_b200/csrc/mf_inflate_par.h"
 
 static uint32_t crc_tab[256];
 static void init_tab() {
@@ -248,6 +249,64 @@ int model_unpack_indexed(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t 
     }
     *produced = op;
     return members ? 0 : MF_DEC_E_TRUNC;
+}
+
+// Block-parallel decoding of a foreign gzip blob, the way the CUDA kernels do it (mf_inflate_par.h), one "lane" at a
+// time: scan every bit position, size the candidates, walk the chain, decode into 16-bit symbols, resolve, verify.
+// Returns 0 / MF_DEC_E_*, or -1 when the chain could not be followed (the product then uses the serial decoder).
+// stats[0] = candidates found, stats[1] = blocks of the chain, stats[2] = markers resolved.
+static uint64_t peek_bits(const uint8_t *src, uint64_t n, uint64_t bitpos, uint32_t count) {
+    uint64_t v = 0;
+    for (uint32_t k = 0; k < count; k++) {
+        const uint64_t b = bitpos + k;
+        if ((b >> 3) >= n) break;
+        v |= (uint64_t)((src[b >> 3] >> (b & 7u)) & 1u) << k;
+    }
+    return v;
+}
+
+int model_gunzip_parallel(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t cap, uint64_t *produced, uint64_t *stats) {
+    init_tab();
+    static MfSpecWork W;
+    std::vector<MfSpecCand> cands;
+    for (uint64_t p = 0; p + 17 <= n * 8ull; p++) {
+        const uint32_t w = (uint32_t)peek_bits(src, n, p, 17);
+        if (!mf_spec_quick(w)) continue;
+        if (!mf_spec_clcode_complete(((w >> 13) & 15u) + 4u, peek_bits(src, n, p + 17, 57))) continue;
+        MfSpecCand c;
+        if (mf_spec_size_block(src, n, p, cap, W, &c) == 0) cands.push_back(c);
+    }
+    std::vector<MfSpecBlock> blocks(cands.size() + n / 5 + 16);
+    std::vector<MfSpecMember> members(n / 18 + 2);
+    uint32_t nb = 0, nm = 0;
+    uint64_t total = 0;
+    int e = mf_spec_walk(src, n, cands.data(), (uint32_t)cands.size(), cap, W, blocks.data(), (uint32_t)blocks.size(), &nb,
+                         members.data(), (uint32_t)members.size(), &nm, &total);
+    if (stats) { stats[0] = cands.size(); stats[1] = nb; stats[2] = 0; }
+    if (e) { if (e == MF_DEC_E_DST) *produced = total; return e; }
+    std::vector<uint16_t> out16(total + 1);
+    for (uint32_t b = 0; b < nb; b++) {
+        e = mf_spec_decode_block(src, n, blocks[b], W, out16.data() + blocks[b].out_off);
+        if (e) return e;
+    }
+    for (uint32_t b = 0; b < nb; b++) {
+        const MfSpecBlock &B = blocks[b];
+        for (uint64_t k = 0; k < B.out_len; k++) {
+            const uint16_t s = out16[B.out_off + k];
+            if (stats && (s & MF_SPEC_MARK)) stats[2]++;
+            const int v = mf_spec_resolve_sym(s, dst, B.out_off, members[B.member].out_off);
+            if (v < 0) return MF_DEC_E_STREAM;
+            dst[B.out_off + k] = (uint8_t)v;
+        }
+    }
+    for (uint32_t m = 0; m < nm; m++) {
+        uint32_t crc = 0xFFFFFFFFu;
+        for (uint64_t k = 0; k < members[m].out_len; k++) crc = crc_tab[(crc ^ dst[members[m].out_off + k]) & 0xFFu] ^ (crc >> 8);
+        if (~crc != members[m].crc_expect) return MF_DEC_E_CRC;
+        if ((uint32_t)(members[m].out_len & 0xFFFFFFFFull) != members[m].isize_expect) return MF_DEC_E_ISIZE;
+    }
+    *produced = total;
+    return 0;
 }
 
 }  // extern "C"

@@ -14,7 +14,8 @@ def lib():
         return _lib
     src = os.path.join(_HERE, "model.cpp")
     csrc = os.path.join(os.path.dirname(_HERE), "..", "metaflow_b200", "csrc")
-    newest = max(os.path.getmtime(p) for p in (src, os.path.join(csrc, "mf_core.h"), os.path.join(csrc, "mf_inflate_core.h")))
+    newest = max(os.path.getmtime(p) for p in (src, os.path.join(csrc, "mf_core.h"), os.path.join(csrc, "mf_inflate_core.h"),
+                                               os.path.join(csrc, "mf_inflate_par.h")))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", _SO, src])
     L = ctypes.CDLL(_SO)
@@ -25,6 +26,7 @@ def lib():
     sig = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
     L.model_gunzip.argtypes = sig
     L.model_unpack_indexed.argtypes = sig
+    L.model_gunzip_parallel.argtypes = sig + [ctypes.POINTER(ctypes.c_uint64)]
     _lib = L
     return L
 
@@ -51,3 +53,12 @@ def gunzip(z, cap):
 
 def unpack_indexed(z, cap):
     return _unp(lib().model_unpack_indexed, z, cap)
+
+
+def gunzip_parallel(z, cap):
+    """-> (error code, bytes, (candidates, chain blocks, markers)) through the block-parallel foreign decoder's model."""
+    out = ctypes.create_string_buffer(max(cap, 1))
+    p = ctypes.c_uint64(0)
+    stats = (ctypes.c_uint64 * 3)()
+    e = lib().model_gunzip_parallel(z, len(z), out, cap, ctypes.byref(p), stats)
+    return e, out.raw[: p.value] if e == 0 else b"", tuple(stats)

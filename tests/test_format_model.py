@@ -114,3 +114,56 @@ def test_corruption_is_detected():
     for cut in (5, 40, len(z) // 2, len(z) - 3):
         assert model_lib.gunzip(bytes(z[:cut]), len(blob))[0] != 0
     assert model_lib.gunzip(os.urandom(64), 1000)[0] != 0
+
+
+def test_block_parallel_foreign_decoder_model():
+    """mf_inflate_par.h (scan -> size -> walk -> decode to 16-bit symbols -> resolve -> verify) on zlib streams of every
+    level, multi-member files, fixed-Huffman and stored blocks, header fields; same bytes as zlib, errors detected."""
+    import io
+    rng = np.random.default_rng(9)
+    text = open(gzip.__file__, "rb").read() * 20
+    cases = dict(_cases())
+    cases["text_long"] = text
+    cases["normal_big"] = rng.standard_normal(400000, dtype=np.float32).tobytes()
+    cases["lowent_big"] = rng.integers(0, 16, 300000).astype(np.float32).tobytes()
+    multi_block = 0
+    for name, blob in cases.items():
+        for level in (0, 1, 3, 6, 9):
+            z = gzip.compress(blob, level)
+            e, out, (ncand, nblocks, nmark) = model_lib.gunzip_parallel(z, len(blob))
+            assert e == 0 and out == blob, (name, level, e)
+            multi_block += nblocks > 1
+            if level >= 3 and name == "lowent_big":
+                assert nblocks >= 2 and nmark > 0, (name, level, nblocks, nmark)     # matches do reach across block boundaries
+    assert multi_block > 10
+    # multi-member + zero padding, FNAME/FEXTRA header fields, fixed Huffman
+    a, b = cases["text"], cases["normal"]
+    z = gzip.compress(a, 9) + gzip.compress(b, 1) + b"\0" * 7 + gzip.compress(b"", 3)
+    e, out, _ = model_lib.gunzip_parallel(z, len(a) + len(b))
+    assert e == 0 and out == a + b
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="named.bin", fileobj=buf, mode="wb", compresslevel=3) as f:
+        f.write(b)
+    e, out, _ = model_lib.gunzip_parallel(buf.getvalue(), len(b))
+    assert e == 0 and out == b
+    co = zlib.compressobj(9, zlib.DEFLATED, 31, 9, zlib.Z_FIXED)
+    data = b"abcabcabc" * 500 + bytes(3000)
+    z = co.compress(data) + co.flush()
+    e, out, (_, nblocks, _) = model_lib.gunzip_parallel(z, len(data))
+    assert e == 0 and out == data
+    # our own files are ordinary gzip too
+    ours = model_lib.pack(cases["normal_big"], 1)
+    e, out, _ = model_lib.gunzip_parallel(ours, len(cases["normal_big"]))
+    assert e == 0 and out == cases["normal_big"]
+    # corruption: CRC, ISIZE, payload, truncation, undersized destination
+    z = bytearray(gzip.compress(cases["normal_big"], 3))
+    z[-6] ^= 1
+    assert model_lib.gunzip_parallel(bytes(z), len(cases["normal_big"]))[0] == 4
+    z[-6] ^= 1; z[-1] ^= 1
+    assert model_lib.gunzip_parallel(bytes(z), len(cases["normal_big"]))[0] == 5
+    z[-1] ^= 1; z[len(z) // 2] ^= 0x40
+    assert model_lib.gunzip_parallel(bytes(z), len(cases["normal_big"]))[0] != 0
+    z[len(z) // 2] ^= 0x40
+    assert model_lib.gunzip_parallel(bytes(z[: len(z) // 2]), len(cases["normal_big"]))[0] != 0
+    e, _, _ = model_lib.gunzip_parallel(bytes(z), len(cases["normal_big"]) - 1)
+    assert e == 1

@@ -315,10 +315,11 @@ def test_c4_nested_256x256_join_loads(gpu_codec, shm_dir):
         fds.ca_store.set_blob_cache(None)
         w = fds.get_task_datastore("1", "inner_join", str(o), attempt=0, mode="w")
         w.init_task()
-        w.save_artifacts(iter([("sums", np.array([float(a.sum(dtype=np.float64)) for a in got]))]))
+        w.save_artifacts(iter([("sums", np.array([float(a.sum(dtype=np.float64)) for a in got])),
+                               ("_foreach_stack", [ForeachFrame("start", "outer", outer, o, o)])]))
         w.done()
         inner_results.append(w)
-    dss = TaskDataStoreSet(fds, "1", steps=["inner_join"], prefetch_data_artifacts=["sums"])
+    dss = TaskDataStoreSet(fds, "1", steps=["inner_join"], prefetch_data_artifacts=["sums", "_foreach_stack"])
     total = {ds.task_id: ds["sums"] for ds in dss}
     fds.ca_store.set_blob_cache(None)
     assert len(total) == outer and all(np.array_equal(total[str(o)], sums[o]) for o in range(outer))
