@@ -131,6 +131,28 @@ MF_HD bool mf_spec_clcode_complete(uint32_t hclen4, uint64_t bits) {
     return sum == 128u;
 }
 
+// Step 1, the full check of one position that passed the cheap tests: the code-length sequence must be well formed
+// and the two codes it describes must be usable (zlib's rules: complete, or a single code of length 1; an end-of-block
+// code).  Needs ~400 bytes of scratch (on the GPU: local memory; it runs for ~0.2 % of the bit positions).
+MF_HD bool mf_spec_header_valid(const uint8_t *src, uint64_t n, uint64_t start_bit) {
+    MfBitReader br; br.init(src, n, start_bit + 3);
+    uint8_t lens[320];
+    uint32_t hlit, hdist;
+    if (mf_read_dynamic_tables(br, lens, hlit, hdist) != 0) return false;
+    for (int pass = 0; pass < 2; pass++) {
+        const uint8_t *l = pass ? lens + hlit : lens;
+        const int cnt = pass ? (int)hdist : (int)hlit;
+        int count[16];
+        for (int i = 0; i < 16; i++) count[i] = 0;
+        for (int s = 0; s < cnt; s++) count[l[s] & 15]++;
+        if (count[0] == cnt) { if (pass == 0) return false; continue; }      // no distance codes at all is fine
+        int left = 1;
+        for (int k = 1; k < 16; k++) { left <<= 1; left -= count[k]; if (left < 0) return false; }
+        if (left > 0 && cnt - count[0] != 1) return false;
+    }
+    return true;
+}
+
 // Step 1 + 2 for one candidate position: parse the header, decode to the end-of-block code, produce nothing.
 // max_out: a block that would make more output than this is not one (bounds the work spent on a false positive).
 MF_HD int mf_spec_size_block(const uint8_t *src, uint64_t n, uint64_t start_bit, uint64_t max_out, MfSpecWork &W, MfSpecCand *out) {

@@ -28,6 +28,7 @@
 #include "mf_deflate.cuh"
 #include "mf_deflate2.cuh"
 #include "mf_inflate.cuh"
+#include "mf_inflate_par.cuh"
 
 #define MFCAS_VERSION_STR "mfcas 0.2 (sm_100a; format MF v1: chunk 32 KiB, segment 1 KiB, member 2 MiB)"
 
@@ -73,7 +74,7 @@ struct WaveCtx {
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_in = nullptr, ev_sha = nullptr, ev_cmp = nullptr, ev_res = nullptr, ev_done = nullptr, ev_shares = nullptr;
     cudaEvent_t tl_start = nullptr, tl_in = nullptr, tl_res = nullptr, tl_done = nullptr;   // timeline (MFCAS_PHASE_TIMING)
-    DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2;
+    DevBuf in_arena, out_arena, d_desc, d_work, slots, phase, phase2, fscratch;
     HostBuf h_desc, h_res;
     // bookkeeping of the submitted wave
     int state = 0;                       // 0 idle, 1 kernels in flight, 2 output D2H in flight
@@ -171,6 +172,8 @@ int device_setup(DeviceState &D) {
     CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEnc2Smem)));
     CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
+    CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
+    CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
     // split differs, and re-splitting needs the SM idle -- with the driver's per-kernel default the hash CTAs wait
     // for the persistent encoder to drain whenever the encoder happens to be dispatched first.  Same split for both.
@@ -190,7 +193,7 @@ void device_teardown(DeviceState &D) {
         if (W.stream) cudaStreamSynchronize(W.stream);
         if (W.stream2) cudaStreamSynchronize(W.stream2);
         W.in_arena.release(); W.out_arena.release(); W.d_desc.release(); W.d_work.release(); W.slots.release();
-        W.phase.release(); W.phase2.release(); W.h_desc.release(); W.h_res.release();
+        W.phase.release(); W.phase2.release(); W.fscratch.release(); W.h_desc.release(); W.h_res.release();
         for (auto &e : W.ev) if (e) cudaEventDestroy(e);
         if (D.tl_origin) { cudaEventDestroy(D.tl_origin); D.tl_origin = nullptr; }
         for (cudaEvent_t e : {W.ev_in, W.ev_sha, W.ev_cmp, W.ev_res, W.ev_shares, W.ev_done, W.tl_start, W.tl_in, W.tl_res, W.tl_done}) if (e) cudaEventDestroy(e);
@@ -583,8 +586,10 @@ int pack_collect(DeviceState &D, WaveCtx &W, uint64_t *dst_len, uint8_t *sha1, i
 }
 
 // ------------------------------------------------------------------ unpack: enqueue (async) / collect
+// `foreign` (may be null): per blob, 1 when the HOST copy of the blob does not start with an 'MF'-indexed member, i.e.
+// a stock gzip stream: those go through the block-parallel foreign decoder (mf_inflate_par.cuh) first.
 int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_src, const uint64_t *src_len,
-                  void *const *d_dst, const uint64_t *dst_cap, const CopyPlan *upload) {
+                  void *const *d_dst, const uint64_t *dst_cap, const CopyPlan *upload, const uint8_t *foreign = nullptr) {
     if (n > 0x7FFFFFFFull) return MFCAS_E_ARG;
     uint64_t max_chunks = 0, max_members = 0;
     for (uint64_t i = 0; i < n; i++) {       // the parse kernel enforces exactly these per-blob quotas
@@ -592,13 +597,33 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
         max_members += qm; max_chunks += dst_cap[i] / MF_CHUNK + qm;
     }
     if (max_chunks > 0x7FFFFFF0ull) return MFCAS_E_ARG;
-    CU(W.h_desc.ensure(sizeof(MfDecBlob) * n));
+    // foreign blobs: descriptors + scratch of the block-parallel decoder
+    std::vector<MfFBlob> fbl;
+    uint64_t total_ranges = 0, out16_syms = 0;
+    if (foreign)
+        for (uint64_t i = 0; i < n; i++) {
+            if (!foreign[i] || src_len[i] < 18 || total_ranges > 0x60000000ull) continue;
+            MfFBlob f;
+            f.src = static_cast<const uint8_t *>(d_src[i]); f.src_len = src_len[i];
+            f.dst = static_cast<uint8_t *>(d_dst[i]); f.dst_cap = dst_cap[i];
+            f.blob = (uint32_t)i;
+            f.range_base = (uint32_t)total_ranges;
+            f.n_ranges = (uint32_t)((src_len[i] + MF_F_RANGE_BYTES - 1) / MF_F_RANGE_BYTES);
+            f.blk_base = (uint32_t)(total_ranges + (uint64_t)fbl.size() * MF_F_EXTRA_BLOCKS);
+            f.out16_off = out16_syms;
+            total_ranges += f.n_ranges; out16_syms += dst_cap[i] + 8;
+            fbl.push_back(f);
+        }
+    const size_t nf = fbl.size();
+    const size_t o_fb = align_up(sizeof(MfDecBlob) * n, 256);
+    CU(W.h_desc.ensure(o_fb + sizeof(MfFBlob) * nf));
     MfDecBlob *hb = W.h_desc.as<MfDecBlob>();
     for (uint64_t i = 0; i < n; i++) {
         hb[i].src = static_cast<const uint8_t *>(d_src[i]); hb[i].src_len = src_len[i];
         hb[i].dst = static_cast<uint8_t *>(d_dst[i]); hb[i].dst_cap = dst_cap[i];
     }
-    CU(W.d_desc.ensure(sizeof(MfDecBlob) * n));
+    if (nf) memcpy(W.h_desc.as<uint8_t>() + o_fb, fbl.data(), sizeof(MfFBlob) * nf);
+    CU(W.d_desc.ensure(o_fb + sizeof(MfFBlob) * nf));
     Carver wc;
     const size_t o_chunks = wc.take(sizeof(MfDecChunk) * max_chunks);
     const size_t o_members = wc.take(sizeof(MfDecMember) * max_members);
@@ -616,7 +641,7 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     uint8_t *dw = W.d_work.as<uint8_t>();
     uint8_t *dres = dw + o_res;
     cudaStream_t s = W.stream;
-    CU(cudaMemcpyAsync(W.d_desc.p, hb, sizeof(MfDecBlob) * n, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(W.d_desc.p, hb, o_fb + sizeof(MfFBlob) * nf, cudaMemcpyHostToDevice, s));
     CU(cudaMemsetAsync(dw + o_kind, 0, (o_res + W.res_bytes) - o_kind, s));     // kind, counters, dst_len, status
     if (upload) {
         if (phase_timing_on()) CU(cudaEventRecord(W.tl_start, s));
@@ -637,6 +662,48 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     mf_verify_kernel<<<(unsigned)((max_members * 32 + 127) / 128), 128, 0, s>>>(
         reinterpret_cast<const MfDecMember *>(dw + o_members), cnt, reinterpret_cast<const uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
+    if (nf) {
+        // ---- block-parallel decoding of the foreign streams (scan, size, walk, decode to 16-bit symbols, resolve, verify);
+        // whatever it cannot follow keeps kind 1 and is decoded by the serial kernel below
+        const uint64_t blk_slots = total_ranges + (uint64_t)nf * MF_F_EXTRA_BLOCKS;
+        Carver fc;
+        const size_t f_cnt = fc.take(sizeof(uint32_t) * total_ranges);
+        const size_t f_pos = fc.take(sizeof(uint64_t) * total_ranges * MF_F_RANGE_SLOTS);
+        const size_t f_cand = fc.take(sizeof(MfSpecCand) * total_ranges);
+        const size_t f_blk = fc.take(sizeof(MfSpecBlock) * blk_slots);
+        const size_t f_mem = fc.take(sizeof(MfSpecMember) * nf * MF_F_MAX_MEMBERS);
+        const size_t f_state = fc.take(sizeof(MfFState) * nf);
+        const size_t f_out16 = fc.take(sizeof(uint16_t) * out16_syms);
+        CU(W.fscratch.ensure(fc.take(0)));
+        uint8_t *fs = W.fscratch.as<uint8_t>();
+        const MfFBlob *dfb = reinterpret_cast<const MfFBlob *>(W.d_desc.as<uint8_t>() + o_fb);
+        MfSpecCand *dcand = reinterpret_cast<MfSpecCand *>(fs + f_cand);
+        MfSpecBlock *dblk = reinterpret_cast<MfSpecBlock *>(fs + f_blk);
+        MfSpecMember *dmem = reinterpret_cast<MfSpecMember *>(fs + f_mem);
+        MfFState *dstate = reinterpret_cast<MfFState *>(fs + f_state);
+        uint8_t *dkind = dw + o_kind;
+        uint64_t *dlen = reinterpret_cast<uint64_t *>(dres + W.r_len);
+        int32_t *dst_status = reinterpret_cast<int32_t *>(dres + W.r_st);
+        const size_t lane_smem = MF_F_LANES * sizeof(MfSpecWork);
+        CU(cudaMemsetAsync(fs + f_cnt, 0, sizeof(uint32_t) * total_ranges, s));
+        mf_fscan_kernel<<<(unsigned)((total_ranges + 127) / 128), 128, 0, s>>>(dfb, (uint32_t)nf, (uint32_t)total_ranges, reinterpret_cast<uint32_t *>(fs + f_cnt),
+                                                                                reinterpret_cast<uint64_t *>(fs + f_pos));
+        CU(cudaGetLastError());
+        mf_fcompact_kernel<<<(unsigned)nf, 1024, 0, s>>>(dfb, reinterpret_cast<const uint32_t *>(fs + f_cnt), reinterpret_cast<const uint64_t *>(fs + f_pos), dcand, dstate);
+        CU(cudaGetLastError());
+        mf_fsize_kernel<<<(unsigned)((total_ranges + MF_F_LANES - 1) / MF_F_LANES), MF_F_LANES, lane_smem, s>>>(dfb, (uint32_t)nf, (uint32_t)total_ranges, dcand, dstate);
+        CU(cudaGetLastError());
+        mf_fwalk_kernel<<<(unsigned)nf, 32, 0, s>>>(dfb, dcand, dstate, dblk, dmem, dkind, dlen, dst_status);
+        CU(cudaGetLastError());
+        mf_fdecode_kernel<<<(unsigned)((blk_slots + MF_F_LANES - 1) / MF_F_LANES), MF_F_LANES, lane_smem, s>>>(dfb, (uint32_t)nf, (uint32_t)blk_slots, dblk, dstate,
+                                                                                                                  reinterpret_cast<uint16_t *>(fs + f_out16));
+        CU(cudaGetLastError());
+        mf_fresolve_kernel<<<(unsigned)nf, 1024, 0, s>>>(dfb, dblk, dmem, dstate, reinterpret_cast<const uint16_t *>(fs + f_out16), dkind, dlen, dst_status);
+        CU(cudaGetLastError());
+        mf_fverify_kernel<<<(unsigned)nf, 1024, 0, s>>>(dfb, dmem, dstate, dkind, dlen, dst_status);
+        CU(cudaGetLastError());
+        D.launches += 7;
+    }
     mf_gunzip_lane_kernel<<<(unsigned)((n + 1) / 2), 64, 0, s>>>(db, (uint32_t)n, dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len),
                                                                   reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
@@ -687,7 +754,17 @@ int wave_submit(mfcas_ctx *ctx, DeviceState &D, WaveCtx &W, const ShardIO &io, s
         up.add(io.src[i], (void *)W.w_src[k], io.src_len[i]);
     }
     int rc;
-    if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), &up);
+    std::vector<uint8_t> foreign;
+    if (io.op == Op::Unpack) {
+        static const bool par = !(getenv("MFCAS_FOREIGN_PARALLEL") && atoi(getenv("MFCAS_FOREIGN_PARALLEL")) == 0);
+        foreign.assign(wn, 0);
+        for (size_t k = 0; par && k < wn; k++) {
+            const uint64_t i = io.sh->idx[pos + k];
+            uint32_t rl, nc;
+            foreign[k] = mf_is_indexed_member(static_cast<const uint8_t *>(io.src[i]), io.src_len[i], &rl, &nc) ? 0 : 1;
+        }
+    }
+    if (io.op == Op::Unpack) rc = unpack_submit(D, W, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), &up, foreign.data());
     else rc = pack_submit(D, W, ctx->flags, wn, W.w_src.data(), W.w_len.data(), W.w_dst.data(), W.w_cap.data(), io.op == Op::Pack, &up);
     if (rc != MFCAS_OK) return rc;
     if (phase_timing_on()) CU(cudaEventRecord(W.tl_res, W.stream));

@@ -273,6 +273,7 @@ int model_gunzip_parallel(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t
         const uint32_t w = (uint32_t)peek_bits(src, n, p, 17);
         if (!mf_spec_quick(w)) continue;
         if (!mf_spec_clcode_complete(((w >> 13) & 15u) + 4u, peek_bits(src, n, p + 17, 57))) continue;
+        if (!mf_spec_header_valid(src, n, p)) continue;
         MfSpecCand c;
         if (mf_spec_size_block(src, n, p, cap, W, &c) == 0) cands.push_back(c);
     }
