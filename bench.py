@@ -412,9 +412,12 @@ def run_ours(args, rank, world, local_rank):
     assert h_out[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes() == h_in[(ne - 1) * stride:(ne - 1) * stride + blob_len].tobytes()
 
     # ---- L-api: objects -> TaskDataStore.save_artifacts -> files on tmpfs -> load_artifacts -> objects,
-    # pickle and filesystem included; a bounded sample of the same arrays (rank 0 only, informational)
+    # pickle and filesystem included; a sample of the same arrays on EVERY rank (its own GPU, its own datastore root on
+    # tmpfs), timed between barriers, aggregated like the other legs (all ranks' bytes / slowest rank's time)
     api = None
-    if rank == 0 and args.api_blobs > 0:
+    api_t = [0.0, 0.0]
+    api_blobs = min(args.api_blobs, n)
+    if api_blobs > 0:
         import shutil
         import tempfile
         from metaflow_b200 import FlowDataStore, LocalStorage
@@ -423,33 +426,39 @@ def run_ours(args, rank, world, local_rank):
         root = tempfile.mkdtemp(prefix="mfcas_api_", dir=base)
         codec = GpuCodec(devices=[local_rank], wave_bytes=args.wave_mib << 20)
         try:
-            arrays = [d_in[i * stride + len(prefix):i * stride + len(prefix) + nbytes].cpu().numpy().view(np.float32).copy() for i in range(args.api_blobs)]
+            arrays = [d_in[i * stride + len(prefix):i * stride + len(prefix) + nbytes].cpu().numpy().view(np.float32).copy() for i in range(api_blobs)]
             fds = FlowDataStore("BenchFlow", storage_impl=LocalStorage, ds_root=root, codec=codec)
             for attempt in range(2):                       # first pass warms the arenas
                 w = fds.get_task_datastore("1", "work", str(attempt), attempt=0, mode="w")
                 w.init_task()
                 shutil.rmtree(os.path.join(root, "BenchFlow", "data"), ignore_errors=True)
+                barrier()
                 t0 = time.perf_counter()
                 w.save_artifacts(((("a%d" % i), a) for i, a in enumerate(arrays)), len_hint=len(arrays))
                 w.done()
                 t1 = time.perf_counter()
+                barrier()
+                t1b = time.perf_counter()
                 r = fds.get_task_datastore("1", "work", str(attempt))
                 back = dict(r.load_artifacts(["a%d" % i for i in range(len(arrays))]))
                 t2 = time.perf_counter()
             assert all(np.array_equal(back["a%d" % i], a) for i, a in enumerate(arrays)), "L-api round trip mismatch"
-            nb = len(arrays) * blob_len
-            api = {"value": nb / (t2 - t0) / 1e9, "unit": UNIT, "save_GBps": nb / (t1 - t0) / 1e9, "load_GBps": nb / (t2 - t1) / 1e9,
-                   "sample": "%d artifacts through TaskDataStore.save_artifacts/load_artifacts, LocalStorage on tmpfs, pickle + files included" % len(arrays)}
+            api_t = [t1 - t0, t2 - t1b]
         finally:
             codec.close()
             shutil.rmtree(root, ignore_errors=True)
 
     # ---- reduce over ranks (max time), aggregate
-    times = torch.tensor([t_save, t_load, e2e_save * 1e3, e2e_load * 1e3] + kms, dtype=torch.float64, device=dev)
+    times = torch.tensor([t_save, t_load, e2e_save * 1e3, e2e_load * 1e3] + api_t + kms, dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     t_save, t_load, e2e_save_ms, e2e_load_ms = (float(x) for x in times[:4])
-    kms = [float(x) for x in times[4:]]
+    api_t = [float(x) for x in times[4:6]]
+    kms = [float(x) for x in times[6:]]
+    if api_blobs > 0 and api_t[0] > 0 and api_t[1] > 0:
+        nb = api_blobs * blob_len * world
+        api = {"value": nb / (api_t[0] + api_t[1]) / 1e9, "unit": UNIT, "save_GBps": nb / api_t[0] / 1e9, "load_GBps": nb / api_t[1] / 1e9,
+               "sample": "%d artifacts per rank through TaskDataStore.save_artifacts/load_artifacts, LocalStorage on tmpfs, pickle + files included" % api_blobs}
     total_raw = raw_bytes * world
     value = total_raw / ((t_save + t_load) * 1e-3) / 1e9
     e2e_value = total_raw / ((e2e_save_ms + e2e_load_ms) * 1e-3) / 1e9
@@ -533,7 +542,7 @@ def main():
     ap.add_argument("--wave-mib", type=int, default=1024, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--api-blobs", type=int, default=64, help="artifacts in the L-api (objects <-> tmpfs files) sample; 0 = skip")
+    ap.add_argument("--api-blobs", type=int, default=512, help="artifacts per rank in the L-api (objects <-> tmpfs files) leg; 0 = skip")
     args = ap.parse_args()
     global ARRAY_ELEMS
     ARRAY_ELEMS = CONFIGS[args.config][0]

@@ -44,6 +44,7 @@ struct MfEnc2Member {
 #define MF2_STAGE_WORDS (32u * MF2_ROW)      // 2176 bytes per warp: the LZ hash table (2 KiB) first, the staged bits afterwards
 #define MF2_LL_MAXBITS 14
 #define MF2_IMG_BYTES (MF_CHUNK + 64u)
+#define MF2_BIAS16 (16.f * 4.f * 0.7213475f)    // 16 (units) * sample weight * 1 / (2 ln 2), per literal symbol in use
 #define MF2_ACCEPT_TOL 128.f                  // codes are kept while they cost at most 1/128 more than fresh ones could
 #define MF2_HIST_STEP 4                       // 8 of a lane's 32 byte positions are sampled, weight 4
 // The sampled positions must not alias with the element size of the data (a stride of 4 over float32 data sees one
@@ -77,6 +78,7 @@ struct __align__(16) MfEnc2Smem {
     uint32_t lit_codes[256 * 8];                    // literal codes, striped over 8 lane groups: [symbol][lane & 7]
     uint32_t crc5[7][32];
     uint32_t crcM[7][32];
+    uint32_t crc8[4][256 * 4];                      // CRCV 1: slice-by-4 byte tables, striped over 4 lane groups: [k][byte][lane & 3]
     uint32_t ll_hist[288];
     uint32_t d_hist[32];
     uint32_t ll_codes[288];
@@ -97,7 +99,7 @@ struct __align__(16) MfEnc2Smem {
     unsigned long long mbar[2];
     uint32_t crc_part[MF2_WARPS];
     uint32_t ticket, total_bits, crc_tail;
-    uint32_t dec_cost, dec_miss, dec_a_ll, dec_b_ll, dec_a_d, dec_b_d;     // this chunk against the codes in use
+    uint32_t dec_cost, dec_miss, dec_used, dec_a_ll, dec_b_ll, dec_a_d, dec_b_d;     // this chunk against the codes in use
 };
 
 static_assert(sizeof(MfEnc2Smem) <= 227u * 1024u, "MfEnc2Smem must fit the 227 KB of shared memory a CTA can have");
@@ -105,6 +107,15 @@ static_assert(sizeof(MfEnc2Smem) <= 227u * 1024u, "MfEnc2Smem must fit the 227 K
 __device__ __forceinline__ uint32_t mf2_fold7(const uint32_t (*T)[32], uint32_t x) {
     return T[0][x & 31u] ^ T[1][(x >> 5) & 31u] ^ T[2][(x >> 10) & 31u] ^ T[3][(x >> 15) & 31u] ^
            T[4][(x >> 20) & 31u] ^ T[5][(x >> 25) & 31u] ^ T[6][x >> 30];
+}
+
+// One slice-by-4 step, x = crc ^ word.  CRCV 0: seven 5-bit slices, conflict-free (27 instructions per word);
+// CRCV 1: four byte slices out of 4-way lane-striped tables (15 instructions, ~2-way bank conflicts).
+template <int CRCV>
+__device__ __forceinline__ uint32_t mf2_crc_step(const MfEnc2Smem &S, uint32_t x, uint32_t lane) {
+    if (CRCV == 0) return mf2_fold7(S.crc5, x);
+    const uint32_t *T = &S.crc8[0][0] + (lane & 3u);
+    return T[3072u + ((x & 0xFFu) << 2)] ^ T[2048u + ((x >> 6) & 0x3FCu)] ^ T[1024u + ((x >> 14) & 0x3FCu)] ^ T[(x >> 22) & 0x3FCu];
 }
 
 // Per-lane staging writer: LSB-first bits into the lane's row of shared memory, starting at bit 0.
@@ -122,7 +133,7 @@ struct Mf2Stage {
         }
         nacc = n2;
     }
-    __device__ __forceinline__ uint32_t finish() { row[wi] = acc; return (wi << 5) + nacc; }
+    __device__ __forceinline__ uint32_t finish() { row[wi] = acc; row[wi + 1] = 0; return (wi << 5) + nacc; }
 };
 
 // One lane's 32-byte span of a segment: literal histogram sample, token packing into the staging row.
@@ -130,7 +141,7 @@ struct Mf2Stage {
 template <bool PACK, bool HIST, uint32_t SAMPLE>
 __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)[8], uint32_t lo, uint32_t hi, const uint32_t *matches,
                                              uint32_t nmatch, uint32_t lane, uint32_t *row) {
-    if (lo >= hi) { if (PACK) row[0] = 0; return 0; }
+    if (lo >= hi) { if (PACK) { row[0] = 0; row[1] = 0; } return 0; }
     uint32_t a = 0, b = nmatch;
     while (a < b) { const uint32_t mid = (a + b) >> 1; if (mf_match_pos(matches[mid]) < lo) a = mid + 1; else b = mid; }
     uint32_t mi = a, p = lo;
@@ -183,10 +194,13 @@ __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)
 
 // LZ77 over one segment by one warp (the parse of mf_deflate.cuh pass 2, literal histogram removed: literals are
 // sampled in the sweep).  ht = 1024 x u16 hash table; returns the number of matches written to ml[].
+// The table is cleared for a member's first chunk only: afterwards it holds whatever the previous chunk left there
+// (its staged bits -- the region is shared), which is a function of the member's own bytes, so the output stays a
+// function of the blob alone; a stale entry is just a candidate that fails the "precedes p and the bytes match" test.
 __device__ __forceinline__ uint32_t mf2_lz_segment(MfEnc2Smem &S, const uint8_t *data, uint32_t base, uint32_t seglen, uint16_t *ht,
-                                                   uint32_t *ml, uint32_t lane, bool lz, uint32_t &dry) {
+                                                   uint32_t *ml, uint32_t lane, bool lz, uint32_t &dry, bool clear) {
     if (!lz) return 0;
-    for (uint32_t i = lane; i < (1u << MF_HASH_BITS) / 2; i += 32) reinterpret_cast<uint32_t *>(ht)[i] = 0;
+    if (clear) for (uint32_t i = lane; i < (1u << MF_HASH_BITS) / 2; i += 32) reinterpret_cast<uint32_t *>(ht)[i] = 0;
     __syncwarp();
     uint32_t nm = 0, pos = 0;
     while (pos < seglen) {
@@ -201,7 +215,7 @@ __device__ __forceinline__ uint32_t mf2_lz_segment(MfEnc2Smem &S, const uint8_t 
         const bool can = (p + MF_MIN_MATCH <= seglen) && (nm < MF_MAXM);
         const uint32_t h = (w * 2654435761u) >> (32 - MF_HASH_BITS);
         int q = -1;
-        if (can) { uint32_t cnd = ht[h]; if (cnd) q = (int)cnd - 1; }
+        if (can) { uint32_t cnd = ht[h]; if (cnd && cnd <= p) q = (int)cnd - 1; }
         __syncwarp();
         if (can) ht[h] = (uint16_t)(p + 1);      // lanes with equal hashes write the same slot: whichever lands is a valid candidate
         __syncwarp();
@@ -261,6 +275,7 @@ __device__ __forceinline__ uint32_t mf2_lz_segment(MfEnc2Smem &S, const uint8_t 
 }
 
 // flags bit 0: MFCAS_FLAG_NO_LZ
+template <int CRCV>
 __global__ void __launch_bounds__(MF2_THREADS, 1)
 mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members, uint64_t *__restrict__ out_len, int32_t *__restrict__ status,
                    uint32_t flags, unsigned long long *__restrict__ phase_clk, uint32_t *__restrict__ ticket) {
@@ -269,6 +284,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const bool lz = (flags & 1u) == 0;
     for (uint32_t i = tid; i < 7 * 32; i += MF2_THREADS) { (&S.crc5[0][0])[i] = (&g_mf_crc5[0][0])[i]; (&S.crcM[0][0])[i] = (&g_mf_crcM[0][0])[i]; }
+    if (CRCV == 1) for (uint32_t i = tid; i < 4096; i += MF2_THREADS) (&S.crc8[0][0])[i] = g_mf_crc_tab[i >> 10][(i >> 2) & 255u];
     if (tid == 0) { mf_mbar_init(&S.mbar[0], 1); mf_mbar_init(&S.mbar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -288,6 +304,10 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
         uint32_t crcB = 0;                         // this thread's Horner accumulator over the full chunks (see header)
         uint32_t dry = 0;
         if (tid == 0) { S.cache_hdr_bits = 0; S.carry = make_uint4(0, 0, 0, 0); S.crc_tail = 0; }
+        for (uint32_t i = tid; i < 288; i += MF2_THREADS) S.ll_hist[i] = 0;
+        if (tid < 32) S.d_hist[tid] = 0;
+        if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_used = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }
+        __syncthreads();
         // first chunk's load
         auto issue_load = [&](uint32_t ci) {
             const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
@@ -305,22 +325,20 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
             const bool last = (ci + 1 == nc);
             if (!last && tid == 0) issue_load(ci + 1);           // buffer b^1 was last read two barriers ago
-            for (uint32_t i = tid; i < 288; i += MF2_THREADS) S.ll_hist[i] = 0;
-            if (tid < 32) S.d_hist[tid] = 0;
-            if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }
+            // (histograms and pricing sums were cleared behind the previous chunk's barriers: no barrier here for a full chunk)
             if (b == 0) { mf_mbar_wait(&S.mbar[0], par0); par0 ^= 1u; } else { mf_mbar_wait(&S.mbar[1], par1); par1 ^= 1u; }
             uint8_t *data = S.data[b];
             if (len < MF_CHUNK) {                                 // bytes past the end: nothing downstream may depend on stale ones
                 if (tid < 64 && len + tid < MF_CHUNK + 64u) data[len + tid] = 0;
+                __syncthreads();
             }
-            __syncthreads();
             MF2_PHASE(1);
 
             // ---- LZ77 + sweep of this warp's segment
             const uint32_t seg = warp, base = seg * MF_SEG;
             const uint32_t seglen = base < len ? min((uint32_t)MF_SEG, len - base) : 0u;
             uint32_t nm = 0;
-            if (seglen) nm = mf2_lz_segment(S, data, base, seglen, reinterpret_cast<uint16_t *>(S.stage[warp]), S.match[seg], lane, lz, dry);
+            if (seglen) nm = mf2_lz_segment(S, data, base, seglen, reinterpret_cast<uint16_t *>(S.stage[warp]), S.match[seg], lane, lz, dry, ci == 0);
             __syncwarp();
             MF2_PHASE(2);
             const uint32_t lo = lane * 32u, hi = min(lo + 32u, seglen);
@@ -333,7 +351,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             if (!last) {
                 uint32_t c = 0;
 #pragma unroll
-                for (int k = 0; k < 8; k++) c = mf2_fold7(S.crc5, c ^ wd[k]);
+                for (int k = 0; k < 8; k++) c = mf2_crc_step<CRCV>(S, c ^ wd[k], lane);
                 crcB = mf2_fold7(S.crcM, crcB) ^ c;
             } else {
                 // the member's last chunk (any length): full 32-byte pieces by table, positioned among the full pieces
@@ -343,7 +361,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 const uint32_t g0 = base + lo;                   // byte offset of this lane's span in the chunk
                 if (g0 + 32u <= len) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) c = mf2_fold7(S.crc5, c ^ wd[k]);
+                    for (int k = 0; k < 8; k++) c = mf2_crc_step<CRCV>(S, c ^ wd[k], lane);
                     c = mf_gf2_mul(c, g_mf_piece32_mul[(len >> 5) - 1u - (g0 >> 5)]);
                 } else if (g0 < len) {
                     uint32_t t = 0;
@@ -385,10 +403,12 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 if (warp < 9) { if (tid < 286) { h = S.ll_hist[tid]; l = S.ll_lens[tid]; } }
                 else if (lane < 30u) { h = S.d_hist[lane]; l = S.d_lens[lane]; }
                 const uint32_t miss = __ballot_sync(0xFFFFFFFFu, h != 0 && l == 0);
+                const uint32_t used = __popc(__ballot_sync(0xFFFFFFFFu, h != 0 && warp < 8));     // literals in use (sampled)
                 const uint32_t cost = mf_warp_sum(h * l), a = mf_warp_sum(h);
                 const uint32_t bb = mf_warp_sum(h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u);
                 if (lane == 0) {
                     atomicAdd(&S.dec_cost, cost);
+                    if (used) atomicAdd(&S.dec_used, used);
                     if (miss) atomicOr(&S.dec_miss, 1u);
                     if (warp < 9) { atomicAdd(&S.dec_a_ll, a); atomicAdd(&S.dec_b_ll, bb); }
                     else { atomicAdd(&S.dec_a_d, a); atomicAdd(&S.dec_b_d, bb); }
@@ -406,6 +426,10 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 float e16 = 0.f;
                 { const uint32_t a = S.dec_a_ll, bsum = S.dec_b_ll; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
                 { const uint32_t a = S.dec_a_d, bsum = S.dec_b_d; if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum; }
+                // the plug-in entropy of a SAMPLED histogram is biased low by (K-1) / (2 ln 2) bits per ... sample set
+                // (K symbols in use); with sample weight 4 that is MF2_BIAS16 units of bits*16 per symbol in use.  The same
+                // term is added where the codes' own redundancy is measured (below), so the two sides stay comparable.
+                e16 += MF2_BIAS16 * (float)S.dec_used;
                 e16 = fmaxf(e16, 0.f);
                 const float nsym = (float)(S.dec_a_ll + S.dec_a_d);
                 accept = have_codes && S.dec_miss == 0 &&
@@ -430,6 +454,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                     float e16 = 0.f;
                     if (a > 1) e16 += (float)a * __log2f((float)a) * 16.f - (float)bsum;
                     if (ad > 1) e16 += (float)ad * __log2f((float)ad) * 16.f - (float)bd;
+                    e16 += MF2_BIAS16 * (float)S.dec_used;
                     e16 = fmaxf(e16, 0.f);
                     const float nsym = (float)(a + ad);
                     if (lane == 0) { S.cache_hdr_bits = hb; S.cache_red16 = nsym > 0.f ? fmaxf((float)own * 16.f - e16, 0.f) / nsym : 0.f; }
@@ -451,6 +476,10 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 __syncthreads();
             }
             MF2_PHASE(5);
+            // the histograms are not read again in this chunk: clear them for the next one (its LZ pass starts behind
+            // barrier 4 below)
+            for (uint32_t i = tid; i < 288; i += MF2_THREADS) S.ll_hist[i] = 0;
+            if (tid < 32) S.d_hist[tid] = 0;
             // ---- chunk size, stored-or-not (every thread computes the same), index entry
             const uint32_t hdr_bits = S.cache_hdr_bits;
             bool stored;
@@ -473,14 +502,13 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                     const uint32_t d0 = cbits + S.seg_off[seg] + lane_off;
                     const uint32_t sh = d0 & 31u, wb = d0 >> 5;
                     const uint32_t *row = S.stage[warp] + lane * MF2_ROW;
-                    const uint32_t nw = (bits + 31u) >> 5;
+                    const uint32_t nout = (bits + sh + 31u) >> 5;                      // image words that get bits of this lane
                     uint32_t prev = 0;
-                    for (uint32_t k = 0; k <= nw; k++) {
-                        if (32u * k >= bits + sh) break;                           // nothing of ours in this word
-                        const uint32_t cur = k < nw ? row[k] : 0u;
-                        const uint32_t v = __funnelshift_l(prev, cur, sh);         // (cur << sh) | (prev >> (32 - sh))
-                        const bool whole = k > 0 && 32u * (k + 1u) <= bits + sh;   // the word holds only this lane's bits
-                        if (whole) S.img[wb + k] = v; else atomicOr(&S.img[wb + k], v);
+                    for (uint32_t k = 0; k < nout; k++) {
+                        const uint32_t cur = row[k];                                   // (one zero word follows the staged ones)
+                        const uint32_t v = __funnelshift_l(prev, cur, sh);             // (cur << sh) | (prev >> (32 - sh))
+                        if (k == 0 || k + 1u == nout) atomicOr(&S.img[wb + k], v);     // shared with the neighbouring lanes
+                        else S.img[wb + k] = v;
                         prev = cur;
                     }
                 }
@@ -548,8 +576,10 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 if (tid == (nv & (MF2_THREADS - 1u))) S.carry = s[nv];               // the partial last vector goes with the next chunk
             }
             woff += comp_bytes;
+            if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_used = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }   // read before barrier 4
             MF2_PHASE(7);
-            __syncthreads();                                     // ---- barrier 5: shared memory is reused by the next chunk
+            // no barrier here: the next chunk touches the image only behind its own barrier 1, and everything else it
+            // writes before that (hash tables / staging rows, match lists, histograms) was last read before barrier 4
 #undef MF2_PHASE
         }
 

@@ -135,6 +135,7 @@ struct Carver {
 };
 
 #define MF_SHA_DEFAULT_VARIANT 0
+#define MF_ENC_DEFAULT_CRC 0
 #define MF_RING 8
 // Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
 // takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
@@ -169,8 +170,10 @@ int device_setup(DeviceState &D) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     CU(cudaFuncSetAttribute(mf_deflate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEncSmem)));
-    CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEnc2Smem)));
-    CU(cudaFuncSetAttribute(mf_deflate2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    for (auto k : {mf_deflate2_kernel<0>, mf_deflate2_kernel<1>}) {
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEnc2Smem)));
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
     CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
@@ -491,7 +494,9 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
             uint64_t *mlen = compact ? reinterpret_cast<uint64_t *>(dw + o_mlen) : reinterpret_cast<uint64_t *>(dres + W.r_len);
             int32_t *mst = compact ? reinterpret_cast<int32_t *>(dw + o_mst) : reinterpret_cast<int32_t *>(dres + W.r_st);
             if (n_members) {
-                mf_deflate2_kernel<<<(unsigned)std::min<uint64_t>(n_members, enc_cap), MF2_THREADS, sizeof(MfEnc2Smem), sc>>>(
+                static const int crcv = getenv("MFCAS_ENC_CRC") ? atoi(getenv("MFCAS_ENC_CRC")) : MF_ENC_DEFAULT_CRC;
+                auto enc = crcv == 1 ? mf_deflate2_kernel<1> : mf_deflate2_kernel<0>;
+                enc<<<(unsigned)std::min<uint64_t>(n_members, enc_cap), MF2_THREADS, sizeof(MfEnc2Smem), sc>>>(
                     reinterpret_cast<const MfEnc2Member *>(dd + o_mem), (uint32_t)n_members, mlen, mst, flags, phase, reinterpret_cast<uint32_t *>(dw + o_ticket));
                 CU(cudaGetLastError());
                 D.launches++;

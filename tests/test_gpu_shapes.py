@@ -307,7 +307,7 @@ def test_c4_nested_256x256_join_loads(gpu_codec, shm_dir):
         got = [ds["x"] for ds in dss]                             # served from the prefetch cache, pathspec order
         assert gpu_codec.counters()["kernel_launches"] == l1
         t_load += time.perf_counter() - t0
-        assert len(got) == inner and 0 < l1 - l0 <= 8             # one batch (parse/inflate/verify/foreign [+ waves])
+        assert len(got) == inner and 0 < l1 - l0 <= 8             # one batch (parse / inflate / verify / serial-foreign)
         assert [float(a.sum(dtype=np.float64)) for a in got] == list(sums[o])
         assert all(a[0] == float(o) and a[1] == float(j) for j, a in enumerate(got))
         if o % 64 == 0:
