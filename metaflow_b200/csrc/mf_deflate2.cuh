@@ -340,6 +340,31 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             uint32_t nm = 0;
             if (seglen) nm = mf2_lz_segment(S, data, base, seglen, reinterpret_cast<uint16_t *>(S.stage[warp]), S.match[seg], lane, lz, dry, ci == 0);
             __syncwarp();
+            const bool have_codes = S.cache_hdr_bits != 0;
+            if (have_codes && nm) {
+                // a match whose length or distance symbol has no code in the codes in use is dropped (its bytes go out as
+                // literals, which always have codes): a rare symbol never forces fresh codes by itself
+                uint32_t kept = 0, dropped = 0;
+                for (uint32_t i0 = 0; i0 < nm; i0 += 32) {
+                    const uint32_t i = i0 + lane;
+                    uint32_t m = 0;
+                    bool ok = false;
+                    if (i < nm) {
+                        m = S.match[seg][i];
+                        uint32_t ls, lb, lv, ds, db, dv;
+                        mf_len_sym(mf_match_len(m), ls, lb, lv); mf_dist_sym(mf_match_dist(m), ds, db, dv);
+                        ok = S.ll_lens[ls] != 0 && S.d_lens[ds] != 0;
+                    }
+                    const uint32_t keep = __ballot_sync(0xFFFFFFFFu, ok);
+                    __syncwarp();
+                    if (ok) S.match[seg][kept + __popc(keep & ((1u << lane) - 1u))] = m;
+                    kept += __popc(keep);
+                    dropped += min(32u, nm - i0) - __popc(keep);
+                    __syncwarp();
+                }
+                nm = kept;
+                if (lane == 0 && dropped) atomicAdd(&S.dec_miss, dropped);
+            }
             MF2_PHASE(2);
             const uint32_t lo = lane * 32u, hi = min(lo + 32u, seglen);
             uint32_t wd[8];
@@ -372,7 +397,6 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 if (lane == 0) S.crc_part[warp] = c;
             }
             uint32_t bits = 0;
-            const bool have_codes = S.cache_hdr_bits != 0;
             if (seglen) {
                 uint32_t *row = S.stage[warp] + lane * MF2_ROW;
                 if (seg & 1u) {
@@ -402,14 +426,12 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 uint32_t h = 0, l = 0;
                 if (warp < 9) { if (tid < 286) { h = S.ll_hist[tid]; l = S.ll_lens[tid]; } }
                 else if (lane < 30u) { h = S.d_hist[lane]; l = S.d_lens[lane]; }
-                const uint32_t miss = __ballot_sync(0xFFFFFFFFu, h != 0 && l == 0);
                 const uint32_t used = __popc(__ballot_sync(0xFFFFFFFFu, h != 0 && warp < 8));     // literals in use (sampled)
                 const uint32_t cost = mf_warp_sum(h * l), a = mf_warp_sum(h);
                 const uint32_t bb = mf_warp_sum(h > 1 ? (uint32_t)((float)h * __log2f((float)h) * 16.f + 0.5f) : 0u);
                 if (lane == 0) {
                     atomicAdd(&S.dec_cost, cost);
                     if (used) atomicAdd(&S.dec_used, used);
-                    if (miss) atomicOr(&S.dec_miss, 1u);
                     if (warp < 9) { atomicAdd(&S.dec_a_ll, a); atomicAdd(&S.dec_b_ll, bb); }
                     else { atomicAdd(&S.dec_a_d, a); atomicAdd(&S.dec_b_d, bb); }
                 }
@@ -432,7 +454,8 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 e16 += MF2_BIAS16 * (float)S.dec_used;
                 e16 = fmaxf(e16, 0.f);
                 const float nsym = (float)(S.dec_a_ll + S.dec_a_d);
-                accept = have_codes && S.dec_miss == 0 &&
+                // (dec_miss = matches dropped for want of a code: tolerated while they are few)
+                accept = have_codes && S.dec_miss * 16u <= S.dec_a_d + 128u &&
                          (float)S.dec_cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / MF2_ACCEPT_TOL) + 1024.f;
             }
             if (!accept) {

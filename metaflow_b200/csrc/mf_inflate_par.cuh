@@ -19,6 +19,7 @@
 #define MF_F_RANGE_SLOTS 2u              // candidates kept per range (more -> the blob falls back to the serial decoder)
 #define MF_F_EXTRA_BLOCKS 64u            // block slots per blob beyond one per range (stored / fixed blocks, tiny streams)
 #define MF_F_MAX_MEMBERS 64u
+#define MF_F_PRE 24u                     // positions a scan thread collects before it validates them
 #define MF_F_LANES 96u                   // decoder lanes per CTA: 2 KiB of tables each
 
 struct MfFBlob {
@@ -30,6 +31,7 @@ struct MfFBlob {
     uint32_t blk_base;        // first block slot (capacity n_ranges + MF_F_EXTRA_BLOCKS)
     uint64_t out16_off;       // first symbol of its region of the 16-bit scratch (capacity dst_cap symbols)
 };
+struct MfSpecLane { MfSpecWork w; uint32_t pad; };   // +4 bytes: lanes at a 2048-byte stride would share one bank (32-way conflicts)
 struct MfFState { uint32_t n_cands, n_blocks, n_members, mode; uint64_t total_out; };   // mode: 0 pending, 1 parallel, 2 fall back, 3 failed
 
 __device__ __forceinline__ uint32_t mf_f_find(const MfFBlob *fb, uint32_t nf, uint32_t slot, bool by_block) {
@@ -52,34 +54,53 @@ __device__ __forceinline__ uint64_t mf_f_load64(const uint8_t *p, const uint8_t 
 __global__ void __launch_bounds__(128)
 mf_fscan_kernel(const MfFBlob *__restrict__ fb, uint32_t nf, uint32_t total_ranges, uint32_t *__restrict__ range_cnt, uint64_t *__restrict__ range_pos) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= total_ranges) return;
-    const MfFBlob B = fb[mf_f_find(fb, nf, r, false)];
-    const uint32_t rl = r - B.range_base;
-    if (rl >= B.n_ranges) return;
+    // (no early return: the warp-wide votes below need every lane)
+    const bool in_grid = r < total_ranges;
+    const MfFBlob B = fb[mf_f_find(fb, nf, in_grid ? r : 0u, false)];
+    const uint32_t rl = (in_grid ? r : 0u) - B.range_base;
+    const bool active = in_grid && rl < B.n_ranges;
     const uint8_t *src = B.src, *end = B.src + B.src_len;
     const uint64_t b0 = (uint64_t)rl * MF_F_RANGE_BYTES;
-    const uint64_t b1 = min(b0 + MF_F_RANGE_BYTES, B.src_len);
+    const uint64_t b1 = active ? min(b0 + MF_F_RANGE_BYTES, B.src_len) : b0;
     uint32_t cnt = 0;
-    uint64_t lo = mf_f_load64(src + b0, end), mid = mf_f_load64(src + b0 + 8, end), hi = 0;
-    for (uint64_t byte = b0; byte < b1; byte += 8) {
-        hi = mf_f_load64(src + byte + 16, end);
-        // bit positions byte*8 .. byte*8+63: the 17 header bits and the 57 code-length-code bits behind them come out of
-        // the 192-bit window (lo, mid, hi)
-        for (uint32_t k = 0; k < 64 && byte * 8 + k + 17 <= B.src_len * 8ull; k++) {
-            const uint64_t w = k ? ((lo >> k) | (mid << (64 - k))) : lo;
-            if (!mf_spec_quick((uint32_t)w & 0x1FFFFu)) continue;
-            const uint64_t w2 = k ? ((mid >> k) | (hi << (64 - k))) : mid;
-            const uint64_t cl = (w >> 17) | (w2 << 47);                       // 57 bits from position + 17
-            if (!mf_spec_clcode_complete((((uint32_t)w >> 13) & 15u) + 4u, cl)) continue;
-            const uint64_t bit = byte * 8 + k;
-            if (byte + (k >> 3) >= b1) break;                                  // belongs to the next range
-            if (!mf_spec_header_valid(src, B.src_len, bit)) continue;
-            if (cnt < MF_F_RANGE_SLOTS) range_pos[(size_t)r * MF_F_RANGE_SLOTS + cnt] = bit;
-            cnt++;
+    // Two phases, so that the expensive check runs converged: first collect the positions that pass the cheap tests
+    // (about 1 in 500) into a small list, then all lanes validate their k-th entry together.  (Validating on the spot
+    // made 31 lanes wait whenever one lane had a hit.)
+    uint16_t pre[MF_F_PRE];
+    uint64_t byte = b0;
+    uint64_t lo = active ? mf_f_load64(src + b0, end) : 0ull, mid = active ? mf_f_load64(src + b0 + 8, end) : 0ull, hi = 0;
+    uint32_t k0 = 0;
+    bool more = active && byte < b1;
+    while (__any_sync(0xFFFFFFFFu, more)) {
+        uint32_t np = 0;
+        while (more && np < MF_F_PRE) {
+            if (k0 == 0) hi = mf_f_load64(src + byte + 16, end);
+            uint32_t k = k0;
+            for (; k < 64 && np < MF_F_PRE; k++) {
+                if (byte * 8 + k + 17 > B.src_len * 8ull || byte + (k >> 3) >= b1) { k = 64; break; }
+                const uint64_t w = k ? ((lo >> k) | (mid << (64 - k))) : lo;
+                if (!mf_spec_quick((uint32_t)w & 0x1FFFFu)) continue;
+                const uint64_t w2 = k ? ((mid >> k) | (hi << (64 - k))) : mid;
+                const uint64_t cl = (w >> 17) | (w2 << 47);                   // 57 bits from position + 17
+                if (!mf_spec_clcode_complete((((uint32_t)w >> 13) & 15u) + 4u, cl)) continue;
+                pre[np++] = (uint16_t)((byte - b0) * 8 + k);
+            }
+            if (k >= 64) { k0 = 0; byte += 8; lo = mid; mid = hi; more = byte < b1; }
+            else k0 = k;                                                      // list full: resume here after validating
         }
-        lo = mid; mid = hi;
+        uint32_t maxn = np;
+        for (int d = 16; d > 0; d >>= 1) maxn = max(maxn, __shfl_xor_sync(0xFFFFFFFFu, maxn, d));
+        for (uint32_t i = 0; i < maxn; i++) {
+            if (i < np) {
+                const uint64_t bit = b0 * 8 + pre[i];
+                if (mf_spec_header_valid(src, B.src_len, bit)) {
+                    if (cnt < MF_F_RANGE_SLOTS) range_pos[(size_t)r * MF_F_RANGE_SLOTS + cnt] = bit;
+                    cnt++;
+                }
+            }
+        }
     }
-    range_cnt[r] = cnt;
+    if (active) range_cnt[r] = cnt;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -118,7 +139,7 @@ mf_fcompact_kernel(const MfFBlob *__restrict__ fb, const uint32_t *__restrict__ 
 __global__ void __launch_bounds__(MF_F_LANES)
 mf_fsize_kernel(const MfFBlob *__restrict__ fb, uint32_t nf, uint32_t total_slots, MfSpecCand *__restrict__ cands, const MfFState *__restrict__ state) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
-    MfSpecWork &W = reinterpret_cast<MfSpecWork *>(mf_smem_raw)[threadIdx.x];
+    MfSpecWork &W = reinterpret_cast<MfSpecLane *>(mf_smem_raw)[threadIdx.x].w;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_slots) return;
     const uint32_t f = mf_f_find(fb, nf, g, false);
@@ -159,7 +180,7 @@ __global__ void __launch_bounds__(MF_F_LANES)
 mf_fdecode_kernel(const MfFBlob *__restrict__ fb, uint32_t nf, uint32_t total_slots, const MfSpecBlock *__restrict__ blocks, MfFState *__restrict__ state,
                   uint16_t *__restrict__ out16) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
-    MfSpecWork &W = reinterpret_cast<MfSpecWork *>(mf_smem_raw)[threadIdx.x];
+    MfSpecWork &W = reinterpret_cast<MfSpecLane *>(mf_smem_raw)[threadIdx.x].w;
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= total_slots) return;
     const uint32_t f = mf_f_find(fb, nf, g, true);

@@ -175,8 +175,8 @@ int device_setup(DeviceState &D) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
-    CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
-    CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecWork))));
+    CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
+    CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
     // split differs, and re-splitting needs the SM idle -- with the driver's per-kernel default the hash CTAs wait
     // for the persistent encoder to drain whenever the encoder happens to be dispatched first.  Same split for both.
@@ -689,7 +689,7 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
         uint8_t *dkind = dw + o_kind;
         uint64_t *dlen = reinterpret_cast<uint64_t *>(dres + W.r_len);
         int32_t *dst_status = reinterpret_cast<int32_t *>(dres + W.r_st);
-        const size_t lane_smem = MF_F_LANES * sizeof(MfSpecWork);
+        const size_t lane_smem = MF_F_LANES * sizeof(MfSpecLane);
         CU(cudaMemsetAsync(fs + f_cnt, 0, sizeof(uint32_t) * total_ranges, s));
         mf_fscan_kernel<<<(unsigned)((total_ranges + 127) / 128), 128, 0, s>>>(dfb, (uint32_t)nf, (uint32_t)total_ranges, reinterpret_cast<uint32_t *>(fs + f_cnt),
                                                                                 reinterpret_cast<uint64_t *>(fs + f_pos));

@@ -3,10 +3,11 @@
 mkdir -p gpurun_out
 {
 echo "=== pytest parity"; S=$(date +%s); timeout 1200 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -s 2>&1 | grep -v "^$" | tail -12; echo "elapsed $(( $(date +%s) - S )) s"
-for crc in 0 1; do
+for crc in 0; do
 echo "=== phase profile v2 crc=$crc"; MFCAS_ENC_CRC=$crc MFCAS_PHASE_TIMING=1 timeout 600 python bench.py --blobs-per-step 64 --steps 1 --warmup 1 --no-cpu-baseline --api-blobs 0 2>&1 | grep "phase\] deflate" | tail -2 | head -1
 echo "=== bench C2 crc=$crc"; MFCAS_ENC_CRC=$crc timeout 1200 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --api-blobs 0 2>gpurun_out/c2v2.err | tee gpurun_out/bench_c2_crc$crc.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['save_GBps'], d['load_GBps'], d['config']['packed_ratio'], d['kernel_ms_per_step'], d['e2e'])"; tail -3 gpurun_out/c2v2.err
 done
+echo "=== ncu deflate2"; timeout 1500 ncu --set full --clock-control none --import-source on -k regex:mf_deflate2_kernel -s 1 -c 1 -o gpurun_out/r02_deflate2b -f python bench.py --blobs-per-step 64 --steps 1 --warmup 1 --no-cpu-baseline --api-blobs 0 > gpurun_out/ncu_d2.log 2>&1; tail -1 gpurun_out/ncu_d2.log | cut -c1-200
 echo "=== bench C2 3072 blobs/step"; timeout 1200 python bench.py --blobs-per-step 3072 --steps 2 --warmup 1 --no-cpu-baseline --api-blobs 0 2>gpurun_out/c2b.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['save_GBps'], d['load_GBps'], d['kernel_ms_per_step'])"; tail -3 gpurun_out/c2b.err
 echo "=== foreign decode launch list"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:mf_ -c 200 --csv --log-file gpurun_out/r02_foreign_launches.csv python tools/foreign_decode.py > gpurun_out/ncu_foreign.log 2>&1; tail -3 gpurun_out/ncu_foreign.log
