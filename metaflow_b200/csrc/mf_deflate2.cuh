@@ -154,7 +154,7 @@ __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)
         // literal-only span: no token bookkeeping; two literals are joined (<= 28 bits) before they reach the writer
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-            const uint32_t b0 = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu, b1 = (wd[k >> 2] >> (((k + 1) & 3) * 8)) & 0xFFu;
+            const uint32_t b0 = __byte_perm(wd[k >> 2], 0u, 0x4440u + (k & 3)), b1 = __byte_perm(wd[k >> 2], 0u, 0x4440u + ((k + 1) & 3));   // PRMT
             if (HIST && ((SAMPLE >> k) & 1u)) atomicAdd(&S.ll_hist[b0], (uint32_t)MF2_HIST_STEP);
             if (HIST && ((SAMPLE >> (k + 1)) & 1u)) atomicAdd(&S.ll_hist[b1], (uint32_t)MF2_HIST_STEP);
             if (PACK) {
@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t mf2_span(MfEnc2Smem &S, const uint32_t (&wd)
                 p += len; mi++;
                 next_pos = mi < nmatch ? mf_match_pos(matches[mi]) : 0xFFFFFFFFu;
             } else {
-                const uint32_t byte = (wd[k >> 2] >> ((k & 3) * 8)) & 0xFFu;
+                const uint32_t byte = __byte_perm(wd[k >> 2], 0u, 0x4440u + (k & 3));
                 if (HIST && ((SAMPLE >> k) & 1u)) atomicAdd(&S.ll_hist[byte], (uint32_t)MF2_HIST_STEP);
                 if (PACK) { const uint32_t e = lit[byte * 8u]; w.put(e & 0xFFFFu, e >> 16); }
                 p++;
@@ -307,6 +307,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
         for (uint32_t i = tid; i < 288; i += MF2_THREADS) S.ll_hist[i] = 0;
         if (tid < 32) S.d_hist[tid] = 0;
         if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_used = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }
+        { uint4 *z = reinterpret_cast<uint4 *>(S.img); for (uint32_t i = tid; i < MF2_IMG_BYTES / 16; i += MF2_THREADS) z[i] = make_uint4(0, 0, 0, 0); }
         __syncthreads();
         // first chunk's load
         auto issue_load = [&](uint32_t ci) {
@@ -414,11 +415,8 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             MF2_PHASE(3);
             __syncthreads();                                     // ---- barrier 1: histograms, staged bits, segment lengths complete
 
-            // zero the image (the previous chunk's stores have read it) and put the carried bytes in front
-            {
-                uint4 *z = reinterpret_cast<uint4 *>(S.img);
-                for (uint32_t i = tid; i < MF2_IMG_BYTES / 16; i += MF2_THREADS) z[i] = (i == 0) ? S.carry : make_uint4(0, 0, 0, 0);
-            }
+            // the image is all zero (every thread cleared the vectors it stored): the carried bytes go in front
+            if (tid == 0) reinterpret_cast<uint4 *>(S.img)[0] = S.carry;
             // ---- price the codes in use against this chunk's (sampled) statistics: symbols 0..285 on warps 0..8, distance
             // symbols on warp 9 (integer sums: the verdict must not depend on the order of the atomics); warp 10 meanwhile
             // scans the segment lengths as if the codes are kept
@@ -595,8 +593,10 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 const uint32_t nv = total >> 4;
                 uint4 *g = reinterpret_cast<uint4 *>(mem.dst + (woff & ~15ull));
                 const uint4 *s = reinterpret_cast<const uint4 *>(S.img);
-                for (uint32_t i = tid; i < nv; i += MF2_THREADS) g[i] = s[i];
-                if (tid == (nv & (MF2_THREADS - 1u))) S.carry = s[nv];               // the partial last vector goes with the next chunk
+                uint4 *sz = reinterpret_cast<uint4 *>(S.img);
+                for (uint32_t i = tid; i < nv; i += MF2_THREADS) { g[i] = s[i]; sz[i] = make_uint4(0, 0, 0, 0); }   // stored, then cleared by its owner
+                if (tid == (nv & (MF2_THREADS - 1u))) { S.carry = s[nv]; sz[nv] = make_uint4(0, 0, 0, 0); }       // the partial last vector goes with the next chunk
+                if (tid == ((nv + 1u) & (MF2_THREADS - 1u))) sz[nv + 1u] = make_uint4(0, 0, 0, 0);                  // (a spill-over word of the last token)
             }
             woff += comp_bytes;
             if (tid == 32) { S.dec_cost = 0; S.dec_miss = 0; S.dec_used = 0; S.dec_a_ll = 0; S.dec_b_ll = 0; S.dec_a_d = 0; S.dec_b_d = 0; }   // read before barrier 4
