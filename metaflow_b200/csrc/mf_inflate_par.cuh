@@ -34,6 +34,79 @@ struct MfFBlob {
 struct MfSpecLane { MfSpecWork w; uint32_t pad; };   // +4 bytes: lanes at a 2048-byte stride would share one bank (32-way conflicts)
 struct MfFState { uint32_t n_cands, n_blocks, n_members, mode; uint64_t total_out; };   // mode: 0 pending, 1 parallel, 2 fall back, 3 failed
 
+// Device forms of mf_spec_size_block / mf_spec_decode_block (mf_inflate_par.h keeps the portable ones: the CPU model
+// runs those).  Same tables, same checks, same results; the symbol loop reads the bit stream a 32-bit word at a time with
+// two words of lookahead (MfFastReader) instead of byte by byte -- a lane decoding alone hides no latency, so the
+// length of the per-symbol dependency chain is what its speed is.
+__device__ int mf_spec_symbols_dev(const uint8_t *src, uint64_t n, uint64_t first_sym_bit, const MfSpecWork &W, uint64_t cap, bool exact_cap,
+                                   uint16_t *out16, uint64_t *end_bit, uint64_t *out_len) {
+    const uint64_t avail = n * 8ull - first_sym_bit;
+    MfFastReader fr; fr.init(src, first_sym_bit, src + n);
+    uint64_t op = 0;
+    for (;;) {
+        fr.fill();
+        const uint32_t e = W.lut.e[fr.peek(MF_GEN_LUT_BITS)];
+        int sym;
+        if (e) { sym = (int)(e & 511u); fr.drop(e >> 9); }
+        else { sym = mf_canon_decode_fast(fr, W.ll.count, W.ll.symbol); if (sym < 0) return fr.used > avail ? MF_DEC_E_TRUNC : MF_DEC_E_STREAM; }
+        if (sym < 256) {
+            if (op >= cap) return exact_cap ? MF_DEC_E_STREAM : MF_DEC_E_DST;
+            if (out16) out16[op] = (uint16_t)sym;
+            op++;
+            continue;
+        }
+        if (fr.used > avail) return MF_DEC_E_TRUNC;
+        if (sym == 256) break;
+        sym -= 257;
+        if (sym >= 29) return MF_DEC_E_STREAM;
+        fr.fill();
+        const uint32_t len = mf_lbase(sym) + fr.get(mf_lext(sym));
+        fr.fill();
+        const int ds = mf_canon_decode_fast(fr, W.dd.count, W.dd.symbol);
+        if (ds < 0 || ds >= 30) return fr.used > avail ? MF_DEC_E_TRUNC : MF_DEC_E_STREAM;
+        fr.fill();
+        const uint32_t dist = mf_dbase(ds) + fr.get(mf_dext(ds));
+        if (fr.used > avail) return MF_DEC_E_TRUNC;
+        if (dist > op + 32768u) return MF_DEC_E_STREAM;          // reaches further back than any window allows
+        if (op + len > cap) return exact_cap ? MF_DEC_E_STREAM : MF_DEC_E_DST;
+        if (out16) {
+            for (uint32_t k = 0; k < len; k++) {
+                uint16_t v;
+                if (dist <= op) v = out16[op - dist];
+                else v = (uint16_t)(MF_SPEC_MARK | (uint32_t)(dist - op - 1u));     // that many bytes before the block's first byte
+                out16[op++] = v;
+            }
+        } else op += len;
+    }
+    *end_bit = first_sym_bit + fr.used;
+    *out_len = op;
+    return 0;
+}
+
+__device__ int mf_spec_size_block_dev(const uint8_t *src, uint64_t n, uint64_t start_bit, uint64_t max_out, MfSpecWork &W, MfSpecCand *out) {
+    MfBitReader br; br.init(src, n, start_bit);
+    uint32_t last = 0;
+    const int e = mf_spec_dynamic_tables(br, W, &last);
+    if (e) return e;
+    uint64_t end_bit = 0, made = 0;
+    const int e2 = mf_spec_symbols_dev(src, n, br.bitpos(), W, max_out, false, nullptr, &end_bit, &made);
+    if (e2) return e2;
+    out->start_bit = start_bit; out->end_bit = end_bit; out->out_len = made;
+    out->flags = MF_SPEC_F_VALID | (last ? MF_SPEC_F_FINAL : 0u);
+    out->pad = 0;
+    return 0;
+}
+
+__device__ int mf_spec_decode_block_dev(const uint8_t *src, uint64_t n, const MfSpecBlock &blk, MfSpecWork &W, uint16_t *out16) {
+    MfBitReader br; br.init(src, n, blk.start_bit);
+    if (blk.kind == MF_BLK_FIXED) { br.get(3); mf_spec_fixed_tables(W); }
+    else { uint32_t last; const int e = mf_spec_dynamic_tables(br, W, &last); if (e) return e; }
+    uint64_t end_bit = 0, made = 0;
+    const int e2 = mf_spec_symbols_dev(src, n, br.bitpos(), W, blk.out_len, true, out16, &end_bit, &made);
+    if (e2) return e2;
+    return made == blk.out_len ? 0 : MF_DEC_E_STREAM;
+}
+
 __device__ __forceinline__ uint32_t mf_f_find(const MfFBlob *fb, uint32_t nf, uint32_t slot, bool by_block) {
     uint32_t lo = 0, hi = nf;                  // last blob whose base <= slot
     while (hi - lo > 1) {
@@ -148,7 +221,7 @@ mf_fsize_kernel(const MfFBlob *__restrict__ fb, uint32_t nf, uint32_t total_slot
     if (state[f].mode != 0 || i >= state[f].n_cands) return;
     MfSpecCand c;
     const uint64_t start = cands[g].start_bit;
-    if (mf_spec_size_block(B.src, B.src_len, start, B.dst_cap, W, &c) == 0) cands[g] = c;       // otherwise flags stay 0: not a block
+    if (mf_spec_size_block_dev(B.src, B.src_len, start, B.dst_cap, W, &c) == 0) cands[g] = c;       // otherwise flags stay 0: not a block
 }
 
 __global__ void __launch_bounds__(32)
@@ -194,7 +267,7 @@ mf_fdecode_kernel(const MfFBlob *__restrict__ fb, uint32_t nf, uint32_t total_sl
         for (uint64_t k = 0; k < blk.out_len; k++) d[k] = p[k];
         return;
     }
-    if (mf_spec_decode_block(B.src, B.src_len, blk, W, out16 + B.out16_off + blk.out_off) != 0) atomicExch(&state[f].mode, 4u);   // resolve reports it
+    if (mf_spec_decode_block_dev(B.src, B.src_len, blk, W, out16 + B.out16_off + blk.out_off) != 0) atomicExch(&state[f].mode, 4u);   // resolve reports it
 }
 
 __global__ void __launch_bounds__(1024)
