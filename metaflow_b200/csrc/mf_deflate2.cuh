@@ -207,8 +207,9 @@ __device__ __forceinline__ uint32_t mf2_lz_segment(MfEnc2Smem &S, const uint8_t 
         const uint32_t p = pos + lane;
         const bool valid = p < seglen;
         // incompressible stretches: the longer nothing matched, the fewer windows are probed (every 4th after 3 dry
-        // windows, every 8th after 6, every 16th after 12); `dry` is carried across the warp's chunks of the member
-        const uint32_t stride = dry >= 12u ? 512u : dry >= 6u ? 256u : 128u;
+        // windows, every 8th after 6, every 16th after 12, one per segment after 48); `dry` is carried across the warp's
+        // chunks of the member
+        const uint32_t stride = dry >= 48u ? 1024u : dry >= 12u ? 512u : dry >= 6u ? 256u : 128u;
         if (dry >= 3u && (pos & (stride - 32u)) != 0) { pos = min(seglen, (pos + stride) & ~(stride - 1u)); continue; }
         const uint32_t nm_before = nm;
         const uint32_t w = valid ? mf_ld32u(data, base + p) : 0u;
