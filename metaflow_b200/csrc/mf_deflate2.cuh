@@ -326,6 +326,9 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             const uint32_t b = ci & 1u;
             const uint32_t len = min((uint32_t)MF_CHUNK, mem.raw_len - ci * MF_CHUNK);
             const bool last = (ci + 1 == nc);
+            // a chunk of at most one segment (the ragged end of a blob, or a tiny blob) is stored: a dynamic block's header
+            // alone is ~90 bytes, and pricing / building codes for it costs more than encoding a full chunk
+            const bool tiny = len <= MF_SEG;
             if (!last && tid == 0) issue_load(ci + 1);           // buffer b^1 was last read two barriers ago
             // (histograms and pricing sums were cleared behind the previous chunk's barriers: no barrier here for a full chunk)
             if (b == 0) { mf_mbar_wait(&S.mbar[0], par0); par0 ^= 1u; } else { mf_mbar_wait(&S.mbar[1], par1); par1 ^= 1u; }
@@ -340,7 +343,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
             const uint32_t seg = warp, base = seg * MF_SEG;
             const uint32_t seglen = base < len ? min((uint32_t)MF_SEG, len - base) : 0u;
             uint32_t nm = 0;
-            if (seglen) nm = mf2_lz_segment(S, data, base, seglen, reinterpret_cast<uint16_t *>(S.stage[warp]), S.match[seg], lane, lz, dry, ci == 0);
+            if (seglen && !tiny) nm = mf2_lz_segment(S, data, base, seglen, reinterpret_cast<uint16_t *>(S.stage[warp]), S.match[seg], lane, lz, dry, ci == 0);
             __syncwarp();
             const bool have_codes = S.cache_hdr_bits != 0;
             if (have_codes && nm) {
@@ -399,7 +402,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 if (lane == 0) S.crc_part[warp] = c;
             }
             uint32_t bits = 0;
-            if (seglen) {
+            if (seglen && !tiny) {
                 uint32_t *row = S.stage[warp] + lane * MF2_ROW;
                 if (seg & 1u) {
                     if (have_codes) bits = mf2_span<true, true, MF2_SAMPLE_B>(S, wd, lo, hi, S.match[seg], nm, lane, row);
@@ -454,8 +457,8 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 e16 = fmaxf(e16, 0.f);
                 const float nsym = (float)(S.dec_a_ll + S.dec_a_d);
                 // (dec_miss = matches dropped for want of a code: tolerated while they are few)
-                accept = have_codes && S.dec_miss * 16u <= S.dec_a_d + 128u &&
-                         (float)S.dec_cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / MF2_ACCEPT_TOL) + 1024.f;
+                accept = tiny || (have_codes && S.dec_miss * 16u <= S.dec_a_d + 128u &&
+                                  (float)S.dec_cost * 16.f <= (e16 + S.cache_red16 * nsym) * (1.f + 1.f / MF2_ACCEPT_TOL) + 1024.f);
             }
             if (!accept) {
                 // ---- fresh codes, then pack again.  They are built from EXACT literal counts: codes fitted to the 1-in-4
@@ -517,7 +520,7 @@ mf_deflate2_kernel(const MfEnc2Member *__restrict__ members, uint32_t n_members,
                 const uint32_t eob = S.ll_codes[256];
                 const uint32_t end_bits = S.total_bits + (eob >> 16) + 3u;          // + empty stored block header (000)
                 const uint32_t dyn_bytes = ((end_bits + 7u) >> 3) + 4u;             // + LEN/NLEN of the sync marker
-                stored = dyn_bytes >= len + 5u;
+                stored = tiny || dyn_bytes >= len + 5u;
                 comp_bytes = stored ? len + 5u : dyn_bytes;
             }
             if (warp == 11) {

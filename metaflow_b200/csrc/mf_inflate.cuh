@@ -250,7 +250,38 @@ struct MfFastReader {
     __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
 };
 
-__device__ __forceinline__ int mf_canon_decode_fast(MfFastReader &br, const uint16_t *count, const uint16_t *symbol) {
+// The chunk decoder's reader: same 64-bit buffer and two words of lookahead, but 32-bit bookkeeping (a segment holds at most
+// 16 K bits, a blob's word index fits 32 bits) and a word INDEX instead of a 64-bit pointer: `fill()` ran for every symbol and
+// was a quarter of the decoder's instructions (ncu, profiles/r02_*), most of them 64-bit compares and adds.
+struct MfSegReader {
+    const uint32_t *base;      // aligned word that holds the blob's first byte
+    uint32_t idx, lim;         // next word to fetch; first word index that must not be read
+    uint64_t buf;
+    uint32_t cnt;
+    uint32_t n0, n1;
+    uint32_t used;             // bits consumed since init
+    __device__ __forceinline__ uint32_t fetch() { const uint32_t v = idx < lim ? __ldg(base + idx) : 0u; idx++; return v; }
+    __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos, const uint8_t *limit) {
+        const uint8_t *a = src + (bitpos >> 3);
+        const uintptr_t al = (uintptr_t)a & ~(uintptr_t)3;
+        const uint32_t skip = (uint32_t)((uintptr_t)a - al) * 8u + (uint32_t)(bitpos & 7u);
+        base = reinterpret_cast<const uint32_t *>(al);
+        idx = 0;
+        lim = (uint32_t)(((((uintptr_t)limit + 3u) & ~(uintptr_t)3) - al) >> 2);
+        buf = (uint64_t)fetch() >> skip;
+        cnt = 32u - skip;
+        buf |= (uint64_t)fetch() << cnt; cnt += 32u;
+        n0 = fetch(); n1 = fetch();
+        used = 0;
+    }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)n0 << cnt; cnt += 32u; n0 = n1; n1 = fetch(); } }
+    __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }
+    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; used += k; }
+    __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
+};
+
+template <typename Reader>
+__device__ __forceinline__ int mf_canon_decode_fast(Reader &br, const uint16_t *count, const uint16_t *symbol) {
     uint32_t bits = (uint32_t)br.buf;
     int code = 0, first = 0, index = 0;
     for (int l = 1; l < 16; l++) {
@@ -408,7 +439,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
             if ((uint64_t)ch.hdr_bits + allbits > (uint64_t)ch.comp_bytes * 8ull) lerr = MF_DEC_E_STREAM;   // index points past the chunk
             else if (seglen) {
                 MfLaneWriter wr; wr.init(ch.dst + seg_base);
-                MfFastReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
+                MfSegReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
                 while (wr.op < seglen) {
                     if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
                     int sym = -2;
@@ -420,7 +451,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                         // the bound on `used` is checked again; the reader itself never leaves the blob.)
 #pragma unroll
                         for (int k = 0; k < 16; k++) {
-                            br.fill();
+                            if ((k & 1) == 0) br.fill();          // > 32 bits in the buffer: enough for two symbols of <= 15 bits
                             const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
                             int s2;
                             if (e) { s2 = (int)(e & 511u); br.drop(e >> 9); }

@@ -491,9 +491,10 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
         } else {
             // the member-owned encoder: one CTA per SM on the SMs the hash CTAs in flight leave free
             // Host waves: stay off the SMs the hash CTAs of the waves in flight need.  The one-wave device-resident call
-            // (gated: the hash CTAs are resident before the encoder is dispatched) asks for every SM: the CTAs that do
-            // not fit wait in the hardware queue and take over the hash CTAs' SMs the moment those finish.
-            const unsigned enc_cap = gate ? 148u : std::max(74u, 148u - std::min(sha_sms, 148u));
+            // asks for every SM (the hash kernel was launched first, on the high-priority stream, and -- up to 64 hash
+            // CTAs -- gated to be resident before the encoder is dispatched): the encoder CTAs that do not fit wait in
+            // the hardware queue and take over the hash CTAs' SMs the moment those finish.
+            const unsigned enc_cap = (gate || !upload) ? 148u : std::max(74u, 148u - std::min(sha_sms, 148u));
             uint64_t *mlen = compact ? reinterpret_cast<uint64_t *>(dw + o_mlen) : reinterpret_cast<uint64_t *>(dres + W.r_len);
             int32_t *mst = compact ? reinterpret_cast<int32_t *>(dw + o_mst) : reinterpret_cast<int32_t *>(dres + W.r_st);
             if (n_members) {
