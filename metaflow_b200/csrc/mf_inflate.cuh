@@ -259,7 +259,7 @@ struct MfSegReader {
     uint64_t buf;
     uint32_t cnt;
     uint32_t n0, n1;
-    uint32_t used;             // bits consumed since init
+    uint32_t fetched;          // bits that entered the buffer since init: bits consumed = fetched - cnt (nothing to keep per symbol)
     __device__ __forceinline__ uint32_t fetch() { const uint32_t v = idx < lim ? __ldg(base + idx) : 0u; idx++; return v; }
     __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos, const uint8_t *limit) {
         const uint8_t *a = src + (bitpos >> 3);
@@ -272,12 +272,13 @@ struct MfSegReader {
         cnt = 32u - skip;
         buf |= (uint64_t)fetch() << cnt; cnt += 32u;
         n0 = fetch(); n1 = fetch();
-        used = 0;
+        fetched = cnt;
     }
-    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)n0 << cnt; cnt += 32u; n0 = n1; n1 = fetch(); } }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)n0 << cnt; cnt += 32u; fetched += 32u; n0 = n1; n1 = fetch(); } }
     __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }
-    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; used += k; }
+    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; }
     __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
+    __device__ __forceinline__ uint32_t used() const { return fetched - cnt; }
 };
 
 template <typename Reader>
@@ -293,7 +294,8 @@ __device__ __forceinline__ int mf_canon_decode_fast(Reader &br, const uint16_t *
     return -1;
 }
 
-__global__ void __launch_bounds__(32 * MF_DEC_WARPS, 5)   // 48 registers, 40 warps per SM: measured best (3: 102 ms, 4: 81 ms, 5: 78 ms, 6: 99 ms per 34 GB)
+template <int MINB>
+__global__ void __launch_bounds__(32 * MF_DEC_WARPS, MINB)   // 5: 48 registers, 40 warps per SM (round 1: 3: 102 ms, 4: 81 ms, 5: 78 ms, 6: 99 ms per 34 GB)
 mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounters *__restrict__ counters,
                         uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
@@ -441,7 +443,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                 MfLaneWriter wr; wr.init(ch.dst + seg_base);
                 MfSegReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
                 while (wr.op < seglen) {
-                    if (br.used > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
+                    if (br.used() > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
                     int sym = -2;
                     if (wr.vec && (wr.op & 15u) == 0 && wr.op + 16u <= seglen) {
                         // Fast path: the next 16 output bytes start a 16-byte window and are (usually) all literals.
@@ -456,7 +458,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                             int s2;
                             if (e) { s2 = (int)(e & 511u); br.drop(e >> 9); }
                             else s2 = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol);
-                            if (s2 >= 256 || s2 < 0) { sym = s2; break; }
+                            if ((uint32_t)s2 >= 256u) { sym = s2; break; }                  // a length / end-of-block symbol, or -1
                             wr.cw |= (uint32_t)s2 << (8 * (k & 3));
                             wr.op++;
                             if ((k & 3) == 3) {
@@ -494,7 +496,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                     if (dist > wr.op || wr.op + len > seglen) { lerr = MF_DEC_E_STREAM; break; }
                     wr.copy_match(len, dist, S.crc_tab);
                 }
-                if (!lerr && br.used != mybits) lerr = MF_DEC_E_STREAM;
+                if (!lerr && br.used() != mybits) lerr = MF_DEC_E_STREAM;
                 crc = wr.finish(S.crc_tab);
             } else if (mybits != 0) lerr = MF_DEC_E_STREAM;
             if (__any_sync(0xFFFFFFFFu, lerr != 0)) err = MF_DEC_E_STREAM;
