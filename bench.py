@@ -389,6 +389,27 @@ def run_ours(args, rank, world, local_rank):
     def refresh(part):
         t_in.copy_(d_in[part * ne * stride:(part + 1) * ne * stride])     # device -> page-locked host buffer (untimed)
 
+    # ---- copy-only ceiling of this box for this rank COUNT: the same page-locked buffers, both directions at once (a save
+    # uploads N while it downloads C, a load the reverse), all ranks at the same time, no kernels.  The e2e number is read
+    # against it: what the copies allow is what the host's memory system and PCIe allow, whatever the kernels do.
+    def copy_probe():
+        x = min(ne * stride, 4 << 30)
+        t_out_h = torch.from_numpy(h_out)
+        sa, sb = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        best = 0.0
+        for _ in range(3):
+            barrier()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            with torch.cuda.stream(sa):
+                ev[0].record(sa); d_in[:x].copy_(t_in[:x], non_blocking=True); ev[1].record(sa)
+            with torch.cuda.stream(sb):
+                ev[2].record(sb); t_out_h[:x].copy_(d_out[:x], non_blocking=True); ev[3].record(sb)
+            torch.cuda.synchronize()
+            ms = max(ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]))
+            best = max(best, x / (ms * 1e-3) / 1e9)
+        return best                                        # GB/s per direction with both directions busy
+
+    both_each = copy_probe()
     generate(20_000); refresh(0); torch.cuda.synchronize(); save_host(); compact_host(); load_host()       # warm-up (arena allocation)
     import gzip
     import hashlib
@@ -453,6 +474,10 @@ def run_ours(args, rank, world, local_rank):
             shutil.rmtree(root, ignore_errors=True)
 
     # ---- reduce over ranks (max time), aggregate
+    probe = torch.tensor([both_each], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(probe, op=dist.ReduceOp.MIN)      # the slowest rank bounds a barrier-to-barrier measurement
+    both_each = float(probe[0])
     times = torch.tensor([t_save, t_load, e2e_save * 1e3, e2e_load * 1e3] + api_t + kms, dtype=torch.float64, device=dev)
     if dist:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -522,7 +547,11 @@ def run_ours(args, rank, world, local_rank):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                     "save_GBps": total_raw / (e2e_save_ms * 1e-3) / 1e9, "load_GBps": total_raw / (e2e_load_ms * 1e-3) / 1e9,
-                    "api": "mfcas_pack_batch_extents + mfcas_unpack_batch on page-locked host buffers"},
+                    "api": "mfcas_pack_batch_extents + mfcas_unpack_batch on page-locked host buffers",
+                    # copies only, both directions busy on every rank at once: per-rank GB/s per direction, and the round-trip
+                    # rate that alone would allow (save = N up | C down, load = C up | N down  ->  about both/2 per rank)
+                    "copy_probe_GBps_each_way_per_rank": both_each, "copy_only_ceiling_GBps": world * both_each / 2.0,
+                    "frac_of_copy_ceiling": e2e_value / (world * both_each / 2.0) if both_each > 0 else None},
             "api": api,
             "gpu_launches": int(launches),
             "clocks": clocks,
