@@ -369,21 +369,29 @@ def run_ours(args, rank, world, local_rank):
         echeck(lib.mfcas_pack_batch_extents(ctx, ne, hsrc, eslen, hpk, epcap, ext_off, ext_len, esha, est), "pack_batch_extents")
         return time.perf_counter() - t0
 
+    hpk_load = (vp * ne)()
+
     def compact_host():
-        """extents -> contiguous packed blob at the start of its slot (what writev into the CAS file does)"""
+        """extents -> one contiguous packed blob each, laid out back to back the way GpuCodec stages files for a load (256-byte
+        aligned slots with a 256-byte gap: the layout the library's device arena uses too, so a wave uploads as one copy).
+        This is what writev into the CAS file + reading the files back does on the real path; not timed."""
         eo = np.frombuffer(ext_off, dtype=np.uint64).reshape(ne, ecount)
         el = np.frombuffer(ext_len, dtype=np.uint64).reshape(ne, ecount)
+        out = 0
         for i in range(ne):
-            base, cur = i * estride, int(el[i, 0])
-            for k in range(1, ecount):
+            base, cur = i * estride, out
+            for k in range(ecount):
                 o, ln = int(eo[i, k]), int(el[i, k])
-                h_pk[base + cur:base + cur + ln] = h_pk[base + o:base + o + ln]
+                if base + o != cur:
+                    h_pk[cur:cur + ln] = h_pk[base + o:base + o + ln]        # always moves towards lower addresses
                 cur += ln
-            eplen[i] = cur
+            eplen[i] = cur - out
+            hpk_load[i] = h_pk_p + out
+            out = (cur + 255) // 256 * 256 + 256
 
     def load_host():
         t0 = time.perf_counter()
-        echeck(lib.mfcas_unpack_batch(ctx, ne, hpk, eplen, hout, eocap, eolen, est), "unpack_batch")
+        echeck(lib.mfcas_unpack_batch(ctx, ne, hpk_load, eplen, hout, eocap, eolen, est), "unpack_batch")
         return time.perf_counter() - t0
 
     def refresh(part):
@@ -415,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
     import hashlib
     blob0 = h_in[:blob_len].tobytes()
     assert esha.raw[:20] == hashlib.sha1(blob0).digest() and h_out[:blob_len].tobytes() == blob0, "e2e parity gate failed"
-    assert gzip.decompress(h_pk[:eplen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"
+    assert gzip.decompress(h_pk[:eplen[0]].tobytes()) == blob0, "reference reader cannot decode the striped blob"   # (blob 0 starts at offset 0)
     barrier()
     ec0 = [u64(0), u64(0), u64(0)]
     lib.mfcas_counters(ctx, *[ctypes.byref(c) for c in ec0])
