@@ -20,6 +20,7 @@
 #include "mf_core.h"
 #include "mf_inflate_core.h"
 #include "mf_deflate.cuh"   // g_mf_crc_tab, g_mf_piece_mul, warp helpers
+#include "mf_deflate2.cuh"  // g_mf_crc5, mf2_fold7: the conflict-free 5-bit CRC slices
 
 struct MfDecBlob {
     const uint8_t *src; uint64_t src_len;
@@ -158,6 +159,7 @@ struct __align__(16) MfDecWarpSmem {
 };
 struct __align__(16) MfDecSmem {
     uint32_t crc_tab[4][256];         // slice-by-4
+    uint32_t crc5[7][32];             // the same step as seven 5-bit slices: conflict-free (DCRC 1, the 16-literal fast path)
     MfDecWarpSmem w[MF_DEC_WARPS];
 };
 
@@ -294,7 +296,7 @@ __device__ __forceinline__ int mf_canon_decode_fast(Reader &br, const uint16_t *
     return -1;
 }
 
-template <int MINB>
+template <int MINB, int DCRC>
 __global__ void __launch_bounds__(32 * MF_DEC_WARPS, MINB)   // 5: 48 registers, 40 warps per SM (round 1: 3: 102 ms, 4: 81 ms, 5: 78 ms, 6: 99 ms per 34 GB)
 mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounters *__restrict__ counters,
                         uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status) {
@@ -302,6 +304,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     MfDecSmem &S = *reinterpret_cast<MfDecSmem *>(mf_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
+    if (DCRC) for (uint32_t i = threadIdx.x; i < 7 * 32; i += blockDim.x) (&S.crc5[0][0])[i] = (&g_mf_crc5[0][0])[i];
     __syncthreads();
     // A warp takes MF_DEC_GROUP consecutive chunks.  The encoder repeats a block header verbatim while the codes
     // of a group stay good, and parsing it (one lane, ~316 code lengths) plus building the LUTs costs almost half
@@ -463,7 +466,8 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                             wr.op++;
                             if ((k & 3) == 3) {
                                 const uint32_t x = wr.crc ^ wr.cw;
-                                wr.crc = S.crc_tab[3][x & 0xFFu] ^ S.crc_tab[2][(x >> 8) & 0xFFu] ^ S.crc_tab[1][(x >> 16) & 0xFFu] ^ S.crc_tab[0][x >> 24];
+                                if (DCRC) wr.crc = mf2_fold7(S.crc5, x);
+                                else wr.crc = S.crc_tab[3][x & 0xFFu] ^ S.crc_tab[2][(x >> 8) & 0xFFu] ^ S.crc_tab[1][(x >> 16) & 0xFFu] ^ S.crc_tab[0][x >> 24];
                                 wr.w[k >> 2] = wr.cw;
                                 wr.cw = 0;
                             }

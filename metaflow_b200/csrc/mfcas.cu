@@ -136,7 +136,8 @@ struct Carver {
 
 #define MF_SHA_DEFAULT_VARIANT 0
 #define MF_ENC_DEFAULT_CRC 0
-#define MF_DEC_DEFAULT_OCC 5
+#define MF_DEC_DEFAULT_OCC 4
+#define MF_DEC_DEFAULT_CRC 0
 #define MF_RING 8
 // Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
 // takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
@@ -175,8 +176,8 @@ int device_setup(DeviceState &D) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfEnc2Smem)));
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
-    CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
-    CU(cudaFuncSetAttribute(mf_inflate_chunk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
+    for (auto k : {mf_inflate_chunk_kernel<5, 0>, mf_inflate_chunk_kernel<4, 0>, mf_inflate_chunk_kernel<4, 1>})
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
     CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
     CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
@@ -667,7 +668,8 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
                                                dw + o_kind, reinterpret_cast<uint64_t *>(dres + W.r_len), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
     static const int dec_occ = getenv("MFCAS_DEC_OCC") ? atoi(getenv("MFCAS_DEC_OCC")) : MF_DEC_DEFAULT_OCC;
-    auto dec_kernel = dec_occ == 4 ? mf_inflate_chunk_kernel<4> : mf_inflate_chunk_kernel<5>;
+    static const int dec_crc = getenv("MFCAS_DEC_CRC") ? atoi(getenv("MFCAS_DEC_CRC")) : MF_DEC_DEFAULT_CRC;
+    auto dec_kernel = dec_occ == 5 ? mf_inflate_chunk_kernel<5, 0> : (dec_crc ? mf_inflate_chunk_kernel<4, 1> : mf_inflate_chunk_kernel<4, 0>);
     dec_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS * MF_DEC_GROUP - 1) / (MF_DEC_WARPS * MF_DEC_GROUP)), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
         reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
     CU(cudaGetLastError());
