@@ -583,7 +583,7 @@ def main():
     ap.add_argument("--wave-mib", type=int, default=1024, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--api-blobs", type=int, default=512, help="artifacts per rank in the L-api (objects <-> tmpfs files) leg; 0 = skip")
+    ap.add_argument("--api-blobs", type=int, default=1024, help="artifacts per rank in the L-api (objects <-> tmpfs files) leg; 0 = skip")
     args = ap.parse_args()
     global ARRAY_ELEMS
     ARRAY_ELEMS = CONFIGS[args.config][0]

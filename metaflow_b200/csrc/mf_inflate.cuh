@@ -39,7 +39,7 @@ struct MfDecChunk {
 struct MfDecMember {
     uint32_t blob, raw_len, crc_expect, first_chunk, n_chunks;
 };
-struct MfDecCounters { uint32_t n_chunks, n_members; };
+struct MfDecCounters { uint32_t n_chunks, n_members, ticket, pad; };   // ticket: next group of chunks to hand out (chunk decoder)
 #define MF_DEC_MIN_MEMBER_RAW (64ull * MF_CHUNK)      // smallest member size our encoders produce for multi-member blobs (2 MiB stripes)
 
 __device__ __forceinline__ void mf_set_status(int32_t *status, uint32_t blob, int32_t err) { atomicCAS(&status[blob], 0, err); }
@@ -139,14 +139,16 @@ mf_parse_kernel(const MfDecBlob *__restrict__ blobs, uint32_t n_blobs, MfDecChun
 
 // ------------------------------------------------------------------ chunk decoder
 #define MF_DEC_WARPS 8
-#define MF_DEC_GROUP 64u      // consecutive chunks per warp (header/LUT reuse)
+#define MF_DEC_GROUP 16u      // default number of consecutive chunks a warp takes per ticket (header/LUT reuse inside it)
 #define MF_LL_LUT_BITS 10
 #define MF_D_LUT_BITS 8
+#define MF_LL_MISS 0x8000u
 
 struct MfCanonSmall { uint16_t count[16]; uint16_t symbol[32]; };
 
 struct __align__(16) MfDecWarpSmem {
-    uint16_t lut_ll[1u << MF_LL_LUT_BITS];   // sym | len << 9 ; 0 = code longer than the LUT
+    uint16_t lut_ll[1u << MF_LL_LUT_BITS];   // literal: byte | len << 8 (so `e < 0x8000` IS the literal test and one PRMT puts the byte in place);
+                                             // length / end-of-block symbol: (sym - 256) | len << 8 | 0x8000; code longer than the table: 0x8000
     uint16_t lut_d[1u << MF_D_LUT_BITS];     // sym | len << 5
     uint8_t lens[320];
     MfCanon ll;
@@ -156,12 +158,15 @@ struct __align__(16) MfDecWarpSmem {
     uint32_t offs_ll[16], offs_d[16];        // running sorted-symbol slot per length
     int32_t err;
     uint32_t hlit, hdist, hdr_end;
+    uint8_t cl_lut[128];                     // code-length code, 7-bit first-level table: sym | len << 5
 };
 struct __align__(16) MfDecSmem {
     uint32_t crc_tab[4][256];         // slice-by-4
     uint32_t crc5[7][32];             // the same step as seven 5-bit slices: conflict-free (DCRC 1, the 16-literal fast path)
     MfDecWarpSmem w[MF_DEC_WARPS];
 };
+// + one 2 KiB input ring per warp (MfRingReader), 2 KiB-aligned behind the struct
+#define MF_DEC_SMEM_BYTES (sizeof(MfDecSmem) + 2048u + MF_DEC_WARPS * 2048u)
 
 // Per-lane output writer: decoded bytes go straight to the lane's 1 KiB segment in HBM, 16 bytes at a
 // time from registers; the raw CRC-32 (slice-by-4) is folded in as every 4-byte word completes.  No
@@ -283,6 +288,70 @@ struct MfSegReader {
     __device__ __forceinline__ uint32_t used() const { return fetched - cnt; }
 };
 
+// The segment decoder's reader.  32 lanes read 32 different streams: a 4-byte load per lane touches 32 different 128-byte
+// lines, and the L1 works such a load off one line per ~2 cycles (B300_MICROARCH.md, "L1tex wavefront queue": 2.07 cycles per
+// wavefront inside one LDG) -- 66 cycles for 128 useful bytes, 1.9 B per cycle per SM = 565 GB/s of packed input for the whole
+// GPU, and the kernel ran at 506 GB/s: THAT was the decoder's bound, not instruction issue (63 ms per 34.4 GB whatever
+// the occupancy, the CRC variant or the ticket size).  So a lane now moves 16 bytes per request: cp.async (LDGSTS.128,
+// no registers, L2 only) into a ring of four 16-byte quads per lane in shared memory, two quads ahead of the one being read;
+// words come out of the ring with conflict-free-enough LDS.32 (bank = 4 * lane + word: 4-way, once per 32 bits).  The ring
+// of a warp is 2 KiB-aligned, so a slot step is arithmetic on the low 11 bits of the address.  Bytes past the end of the
+// blob arrive as zeros (src-size operand), which also makes the per-word limit check unnecessary.
+#define MF_RING_BYTES 2048u
+struct MfRingReader {
+    const uint8_t *g;          // global address of the next quad to bring in (16-byte aligned)
+    uint32_t left;             // readable bytes at g and beyond
+    uint32_t wslot;            // shared address the next quad goes to (slot * 512 + lane * 16)
+    uint32_t raddr;            // shared address of the next word to read
+    uint64_t buf;
+    uint32_t cnt, n0, fetched; // as MfSegReader: bits consumed = fetched - cnt
+    __device__ __forceinline__ void issue() {
+        const uint32_t nb = left < 16u ? left : 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wslot), "l"(g), "r"(nb));
+        asm volatile("cp.async.commit_group;");
+        if (nb == 16u) g += 16;                           // (past the end nothing is read any more: the address stays put)
+        left -= nb;
+        wslot = (wslot & ~(MF_RING_BYTES - 1u)) | ((wslot + 512u) & (MF_RING_BYTES - 1u));
+    }
+    __device__ __forceinline__ uint32_t word() {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(raddr));
+        raddr += 4u;
+        if ((raddr & 15u) == 0) {                         // quad finished: step to the next slot, refill the slot freed ONE step ago
+            raddr = (raddr & ~(MF_RING_BYTES - 1u)) | ((raddr + 496u) & (MF_RING_BYTES - 1u));
+            issue();
+            asm volatile("cp.async.wait_group 2;");       // the quad about to be read has landed (two younger ones may be in flight)
+        }
+        return v;
+    }
+    // ring_lane: shared address of this lane's 16 bytes in slot 0 of its warp's ring
+    __device__ __forceinline__ void init(const uint8_t *src, uint64_t bitpos, const uint8_t *limit, uint32_t ring_lane) {
+        asm volatile("cp.async.wait_group 0;");           // nothing of the previous segment's lookahead may land in the ring any more
+        const uint8_t *a = src + (bitpos >> 3);
+        const uintptr_t al = (uintptr_t)a & ~(uintptr_t)15;
+        const uint32_t skip = (uint32_t)((uintptr_t)a - al) * 8u + (uint32_t)(bitpos & 7u);
+        g = reinterpret_cast<const uint8_t *>(al);
+        const uint64_t room = (uintptr_t)limit > al ? (uint64_t)((uintptr_t)limit - al) : 0ull;
+        left = room > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)room;
+        wslot = ring_lane;
+        raddr = ring_lane + ((skip >> 5) << 2);
+        issue(); issue(); issue();
+        asm volatile("cp.async.wait_group 2;");
+        const uint32_t sb = skip & 31u;
+        buf = (uint64_t)word() >> sb;
+        cnt = 32u - sb;
+        buf |= (uint64_t)word() << cnt; cnt += 32u;
+        n0 = word();
+        fetched = cnt;
+    }
+    __device__ __forceinline__ void fill() { if (cnt <= 32u) { buf |= (uint64_t)n0 << cnt; cnt += 32u; fetched += 32u; n0 = word(); } }
+    __device__ __forceinline__ uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }
+    __device__ __forceinline__ void drop(uint32_t k) { buf >>= k; cnt -= k; }
+    __device__ __forceinline__ uint32_t get(uint32_t k) { uint32_t v = (uint32_t)buf & ((1u << k) - 1u); drop(k); return v; }
+    __device__ __forceinline__ uint32_t used() const { return fetched - cnt; }
+    __device__ __forceinline__ void done() { asm volatile("cp.async.wait_group 0;"); }
+};
+
 template <typename Reader>
 __device__ __forceinline__ int mf_canon_decode_fast(Reader &br, const uint16_t *count, const uint16_t *symbol) {
     uint32_t bits = (uint32_t)br.buf;
@@ -296,27 +365,41 @@ __device__ __forceinline__ int mf_canon_decode_fast(Reader &br, const uint16_t *
     return -1;
 }
 
+// Block header of a chunk through mf_read_header_fast_t (mf_inflate_core.h) with the chunk decoder's word reader.
+__device__ __noinline__ uint32_t mf_read_header_fast(const uint8_t *src, uint32_t comp_bytes, const uint8_t *limit, uint8_t *lens, uint8_t *cl_lut,
+                                                     uint32_t &hlit_out, uint32_t &hdist_out) {
+    MfSegReader br; br.init(src, 0, limit);
+    return mf_read_header_fast_t(br, comp_bytes, lens, cl_lut, hlit_out, hdist_out);
+}
+
 template <int MINB, int DCRC>
 __global__ void __launch_bounds__(32 * MF_DEC_WARPS, MINB)   // 5: 48 registers, 40 warps per SM (round 1: 3: 102 ms, 4: 81 ms, 5: 78 ms, 6: 99 ms per 34 GB)
-mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounters *__restrict__ counters,
-                        uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status) {
+mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__restrict__ counters,
+                        uint32_t *__restrict__ chunk_crc, int32_t *__restrict__ status, uint32_t group) {
     extern __shared__ __align__(16) uint8_t mf_smem_raw[];
     MfDecSmem &S = *reinterpret_cast<MfDecSmem *>(mf_smem_raw);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // the warps' input rings behind the tables, 2 KiB-aligned (MF_DEC_SMEM_BYTES leaves the slack)
+    const uint32_t ring_lane = (((uint32_t)__cvta_generic_to_shared(mf_smem_raw + sizeof(MfDecSmem)) + MF_RING_BYTES - 1u) & ~(MF_RING_BYTES - 1u))
+                               + warp * MF_RING_BYTES + lane * 16u;
     for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) (&S.crc_tab[0][0])[i] = (&g_mf_crc_tab[0][0])[i];
     if (DCRC) for (uint32_t i = threadIdx.x; i < 7 * 32; i += blockDim.x) (&S.crc5[0][0])[i] = (&g_mf_crc5[0][0])[i];
     __syncthreads();
-    // A warp takes MF_DEC_GROUP consecutive chunks.  The encoder repeats a block header verbatim while the codes
-    // of a group stay good, and parsing it (one lane, ~316 code lengths) plus building the LUTs costs almost half
-    // of what decoding the chunk's 32 segments does: when a chunk's header equals the previous chunk's bit for
+    // Resident warps take `group` consecutive chunks at a time by ticket until none are left (round 1: a fixed 64 chunks per
+    // warp of a one-shot grid -- the last, partly filled wave of those 2 MiB tasks cost ~13 % of the kernel).  The encoder
+    // repeats a block header verbatim while the codes stay good; when a chunk's header equals the previous chunk's bit for
     // bit, the tables in shared memory are simply kept.
     const uint32_t n_chunks = counters->n_chunks;
-    const uint32_t c0 = (blockIdx.x * MF_DEC_WARPS + warp) * MF_DEC_GROUP;
-    if (c0 >= n_chunks) return;
-    const uint32_t c1 = min(c0 + MF_DEC_GROUP, n_chunks);
     MfDecWarpSmem &W = S.w[warp];
     const uint8_t *tab_src = nullptr;      // header the tables in W were built from (null: none)
     uint32_t tab_bits = 0;
+    for (;;) {
+    uint32_t c0 = 0;
+    if (lane == 0) c0 = atomicAdd(&counters->ticket, 1u);
+    c0 = __shfl_sync(0xFFFFFFFFu, c0, 0);
+    if ((uint64_t)c0 * group >= n_chunks) break;
+    c0 *= group;
+    const uint32_t c1 = min(c0 + group, n_chunks);
     for (uint32_t c = c0; c < c1; c++) {
     const MfDecChunk ch = chunks[c];
     const uint32_t raw_len = ch.raw_len;
@@ -355,16 +438,19 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
         tab_src = nullptr;
         // ---- block header (lane 0), lengths into smem
         if (lane == 0) {
-            MfBitReader br; br.init(ch.src, ch.comp_bytes, 0);
-            uint32_t bfinal = br.get(1), btype = br.get(2);
             int e = 0;
             uint32_t hlit = 0, hdist = 0;
-            if (bfinal != 0 || btype != 2) e = MF_DEC_E_STREAM;
-            if (!e) e = mf_read_dynamic_tables(br, W.lens, hlit, hdist);
-            if (!e && br.bitpos() != ch.hdr_bits) e = MF_DEC_E_STREAM;
+            const uint32_t fast_bits = mf_read_header_fast(ch.src, ch.comp_bytes, ch.limit, W.lens, W.cl_lut, hlit, hdist);
+            if (fast_bits == 0) {          // anything unusual: the portable parser decides (and names the error)
+                MfBitReader br; br.init(ch.src, ch.comp_bytes, 0);
+                uint32_t bfinal = br.get(1), btype = br.get(2);
+                if (bfinal != 0 || btype != 2) e = MF_DEC_E_STREAM;
+                if (!e) e = mf_read_dynamic_tables(br, W.lens, hlit, hdist);
+                if (!e && br.bitpos() != ch.hdr_bits) e = MF_DEC_E_STREAM;
+            } else if (fast_bits != ch.hdr_bits) e = MF_DEC_E_STREAM;
             W.err = e; W.hlit = hlit; W.hdist = hdist;
         }
-        for (uint32_t i = lane; i < (1u << MF_LL_LUT_BITS); i += 32) W.lut_ll[i] = 0;
+        for (uint32_t i = lane; i < (1u << MF_LL_LUT_BITS); i += 32) W.lut_ll[i] = MF_LL_MISS;
         for (uint32_t i = lane; i < (1u << MF_D_LUT_BITS); i += 32) W.lut_d[i] = 0;
         if (lane < 16) { W.cnt_ll[lane] = 0; W.cnt_d[lane] = 0; }
         __syncwarp();
@@ -411,7 +497,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                     W.ll.symbol[slot] = (uint16_t)s;
                     if (l <= MF_LL_LUT_BITS) {
                         uint32_t rev = __brev(code) >> (32 - l);
-                        uint16_t e = (uint16_t)(s | (l << 9));
+                        const uint16_t e = (uint16_t)(s < 256u ? (s | (l << 8)) : ((s - 256u) | (l << 8) | MF_LL_MISS));
                         for (uint32_t k = rev; k < (1u << MF_LL_LUT_BITS); k += (1u << l)) W.lut_ll[k] = e;
                     }
                 }
@@ -444,7 +530,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
             if ((uint64_t)ch.hdr_bits + allbits > (uint64_t)ch.comp_bytes * 8ull) lerr = MF_DEC_E_STREAM;   // index points past the chunk
             else if (seglen) {
                 MfLaneWriter wr; wr.init(ch.dst + seg_base);
-                MfSegReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit);
+                MfRingReader br; br.init(ch.src, (uint64_t)ch.hdr_bits + incl - mybits, ch.limit, ring_lane);
                 while (wr.op < seglen) {
                     if (br.used() > mybits) { lerr = MF_DEC_E_STREAM; break; }   // bounds every read on corrupt input
                     int sym = -2;
@@ -454,16 +540,21 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                         // one CRC fold per word, one 16-byte store.  A length symbol leaves the loop with the writer
                         // state exact (op, cw, w[]) and is handled below.  (At most 16 x 15 bits are consumed before
                         // the bound on `used` is checked again; the reader itself never leaves the blob.)
+                        const uint32_t op0 = wr.op;
 #pragma unroll
                         for (int k = 0; k < 16; k++) {
                             if ((k & 1) == 0) br.fill();          // > 32 bits in the buffer: enough for two symbols of <= 15 bits
                             const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
-                            int s2;
-                            if (e) { s2 = (int)(e & 511u); br.drop(e >> 9); }
-                            else s2 = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol);
-                            if ((uint32_t)s2 >= 256u) { sym = s2; break; }                  // a length / end-of-block symbol, or -1
-                            wr.cw |= (uint32_t)s2 << (8 * (k & 3));
-                            wr.op++;
+                            if (e < MF_LL_MISS) {                                   // a literal: drop its bits, put its byte in place
+                                br.drop(e >> 8);
+                                wr.cw = __byte_perm(wr.cw, e, (k & 3) == 0 ? 0x3214u : ((k & 3) == 1 ? 0x3240u : ((k & 3) == 2 ? 0x3410u : 0x4210u)));
+                            } else {
+                                int s2;
+                                if (e != MF_LL_MISS) { s2 = 256 + (int)(e & 0xFFu); br.drop((e >> 8) & 0x7Fu); }
+                                else s2 = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol);
+                                if ((uint32_t)s2 >= 256u) { sym = s2; wr.op = op0 + (uint32_t)k; break; }   // a length / end-of-block symbol, or -1
+                                wr.cw |= (uint32_t)s2 << (8 * (k & 3));             // a literal with a code longer than the table
+                            }
                             if ((k & 3) == 3) {
                                 const uint32_t x = wr.crc ^ wr.cw;
                                 if (DCRC) wr.crc = mf2_fold7(S.crc5, x);
@@ -473,15 +564,16 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                             }
                         }
                         if (sym == -2) {       // all 16 were literals
-                            *reinterpret_cast<uint4 *>(wr.dst + wr.op - 16) = make_uint4(wr.w[0], wr.w[1], wr.w[2], wr.w[3]);
+                            wr.op = op0 + 16u;
+                            *reinterpret_cast<uint4 *>(wr.dst + op0) = make_uint4(wr.w[0], wr.w[1], wr.w[2], wr.w[3]);
                             wr.w[0] = wr.w[1] = wr.w[2] = wr.w[3] = 0;
                             continue;
                         }
                         if (sym < 0) { lerr = MF_DEC_E_STREAM; break; }
                     } else {
                         br.fill();
-                        uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
-                        if (e) { sym = (int)(e & 511u); br.drop(e >> 9); }
+                        const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
+                        if (e != MF_LL_MISS) { sym = (int)((e & 0xFFu) + ((e >> 15) << 8)); br.drop((e >> 8) & 0x7Fu); }
                         else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
                         if (sym < 256) { wr.put((uint32_t)sym, S.crc_tab); continue; }
                     }
@@ -501,6 +593,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
                     wr.copy_match(len, dist, S.crc_tab);
                 }
                 if (!lerr && br.used() != mybits) lerr = MF_DEC_E_STREAM;
+                br.done();
                 crc = wr.finish(S.crc_tab);
             } else if (mybits != 0) lerr = MF_DEC_E_STREAM;
             if (__any_sync(0xFFFFFFFFu, lerr != 0)) err = MF_DEC_E_STREAM;
@@ -517,6 +610,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, const MfDecCounte
     }
     crc = mf_warp_xor(crc);
     if (lane == 0) chunk_crc[c] = crc;
+    }
     }
 }
 

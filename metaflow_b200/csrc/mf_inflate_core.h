@@ -139,6 +139,78 @@ MF_HD int mf_read_dynamic_tables(MfBitReader &br, uint8_t *lens, uint32_t &hlit,
     return 0;
 }
 
+// The same parse (BFINAL/BTYPE included), the quick way, for a reader R with a 64-bit buffer and word refills
+// (fill(): more than 32 valid bits afterwards; peek/drop/get without checks; used(): bits consumed; reads past the end
+// of the blob deliver zeros): a 7-bit first-level table for the code-length code instead of the bit-by-bit canonical walk
+// over a byte reader, which cost the chunk decoder almost half of what decoding the chunk's 32 segments does.
+// Returns the header's length in bits, or 0 for ANYTHING unusual -- the caller then runs the parser above, which owns the
+// error codes.  When it returns non-zero, lens / hlit / hdist are exactly what the parser above delivers
+// (tests/test_format_model.py::test_fast_header_parser_equals_the_portable_one).  cl_lut: 128 bytes of scratch.
+MF_HD uint32_t mf_bitrev32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+template <typename R>
+MF_HD uint32_t mf_read_header_fast_t(R &br, uint32_t comp_bytes, uint8_t *lens, uint8_t *cl_lut, uint32_t &hlit_out, uint32_t &hdist_out) {
+    br.fill();
+    if (br.get(3) != 4u) return 0;                        // BFINAL 0, BTYPE 10
+    const uint32_t hlit = br.get(5) + 257u, hdist = br.get(5) + 1u, hclen = br.get(4) + 4u;
+    if (hlit > 286u || hdist > 30u) return 0;
+    // code-length code: lengths in the RFC's order; a complete code is required (mf_canon_build(...) == 0 with a code)
+    const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint8_t cl[19];
+    uint32_t cnt[8], next[8];
+    for (int k = 0; k < 19; k++) cl[k] = 0;
+    for (int k = 0; k < 8; k++) cnt[k] = 0;
+    for (uint32_t i = 0; i < hclen; i++) {
+        if ((i & 7u) == 0) br.fill();                     // 8 x 3 bits per refill
+        const uint32_t l = br.get(3);
+        cl[order[i]] = (uint8_t)l;
+        cnt[l]++;
+    }
+    int left = 1;
+    uint32_t code = 0;
+    next[0] = 0;
+    for (int l = 1; l < 8; l++) { code = (code + (l > 1 ? cnt[l - 1] : 0u)) << 1; next[l] = code; left = (left << 1) - (int)cnt[l]; }
+    if (left != 0) return 0;
+    for (uint32_t s = 0; s < 19u; s++) {
+        const uint32_t l = cl[s];
+        if (!l) continue;
+        const uint32_t c = next[l]++;
+        const uint32_t rev = mf_bitrev32(c) >> (32u - l);
+        const uint8_t ent = (uint8_t)(s | (l << 5));
+        for (uint32_t k = rev; k < 128u; k += (1u << l)) cl_lut[k] = ent;
+    }
+    const uint32_t tot = hlit + hdist;
+    uint32_t i = 0, prev = 0;
+    while (i < tot) {
+        br.fill();                                        // > 32 bits: a code (<= 7) and its extra bits (<= 7)
+        const uint32_t e = cl_lut[br.peek(7)];
+        const uint32_t sym = e & 31u;
+        br.drop(e >> 5);
+        if (sym < 16u) { lens[i++] = (uint8_t)sym; prev = sym; continue; }
+        uint32_t v = 0, rep;
+        if (sym == 16u) { if (i == 0) return 0; v = prev; rep = 3u + br.get(2); }
+        else if (sym == 17u) rep = 3u + br.get(3);
+        else rep = 11u + br.get(7);
+        if (i + rep > tot) return 0;
+        for (uint32_t k = 0; k < rep; k++) lens[i + k] = (uint8_t)v;
+        i += rep; prev = v;
+    }
+    if (lens[256] == 0) return 0;
+    const uint32_t used = br.used();
+    if ((uint64_t)used > (uint64_t)comp_bytes * 8ull) return 0;
+    hlit_out = hlit; hdist_out = hdist;
+    return used;
+}
+
 // Whole raw-DEFLATE stream, one lane.  dst doubles as the 32 KiB window.
 // tables of one serial inflater.  The caller decides where they live: on the GPU a per-thread (local-memory) copy is
 // interleaved with the other threads' at a 128-byte stride -- a 1 KiB table is 256 cache lines and every lookup

@@ -49,6 +49,7 @@ struct __align__(16) MfShaSmem {
     uint8_t raw[2][2][32][MF_SHA_ROW];    // [producer][group parity][stream][bytes]
     uint32_t kw[2][2][32][MF_SHA_KWROW];  // [producer][slot][stream][round]: two blocks of slack per producer
     unsigned long long mbar[2][2];        // [producer][group parity]: TMA bulk-copy completion barriers
+    unsigned long long full[2][2];        // [producer][slot]: (K+W) slot filled (VARIANT 4: mbarrier instead of a named barrier)
 };
 
 // Named barriers: unit u uses ids 8u .. 8u+7 = FULL / EMPTY per (producer, slot).  A producer owns two (K+W)
@@ -86,11 +87,19 @@ __device__ __forceinline__ void mf_mbar_wait(void *bar, uint32_t parity) {
     }
 }
 
+// non-blocking test of a phase (the result can be looked at many instructions later), and the blocking wait
+__device__ __forceinline__ uint32_t mf_mbar_test(void *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(mf_smem_u32(bar)), "r"(parity) : "memory");
+    return ok;
+}
+
 struct MfShaLane {               // what a lane knows about its stream in this launch
     const uint8_t *src; uint64_t len, nfull, nb, iters, bits; uint32_t r; bool valid, is_last, is_first;
 };
 
 // ------------------------------------------------------------------ producer PID of unit UNIT: blocks PID, PID+2, ...
+template <bool MBAR>
 __device__ __forceinline__ void mf_sha_produce(MfShaSmem &S, const MfShaLane &L, const uint32_t UNIT, const uint32_t PID, uint32_t lane, unsigned long long *dbg_out) {
     const uint8_t *src = L.src;
     const uint64_t len = L.len, iters = L.iters;
@@ -163,7 +172,8 @@ __device__ __forceinline__ void mf_sha_produce(MfShaSmem &S, const MfShaLane &L,
 #undef MF_W
         // no fence: bar.arrive orders this thread's prior shared-memory stores for the barrier's
         // participants (the PTX producer/consumer idiom); a MEMBAR here would drain every store
-        mf_bar_arrive_r(MF_BAR_FULL(UNIT, PID, SLOT));
+        if (MBAR) mf_mbar_arrive(&S.full[PID][SLOT]);      // release: this lane's stores above are visible to whoever sees the phase
+        else mf_bar_arrive_r(MF_BAR_FULL(UNIT, PID, SLOT));
         // this producer is done with group g once it has taken its last block of it (blocks 6 or 7)
         if ((i & 7) >= 6) issue_group(g + 2);
     }
@@ -181,9 +191,26 @@ __device__ __forceinline__ void mf_sha_consume(MfShaSmem &S, const MfShaLane &L,
     }
     long long cwait = 0, cstart = dbg_out ? clock64() : 0;
     const uint64_t iters = L.iters, nb = L.nb;
+    // VARIANT 4: the hand-over costs the lone consumer warp ~180 of its ~840 cycles per block (a blocking bar.sync, then the
+    // first LDS of the new block before a round can start).  Here the FULL side is an mbarrier: the phase of block i+1 is
+    // TESTED (non-blocking) 40 rounds before block i ends, looked at 20 rounds later, and the (K+W) words of the next
+    // block's first 20 rounds are loaded under the last 20 rounds of this one.
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0, n4 = n0;
+    auto full_wait = [&](uint64_t blk) {
+        void *bar = &S.full[blk & 1u][(blk >> 1) & 1u];
+        const uint32_t par = (uint32_t)(blk >> 2) & 1u;
+        long long t0_ = dbg_out ? clock64() : 0;
+        mf_mbar_wait(bar, par);
+        if (dbg_out) cwait += clock64() - t0_;
+    };
+    if (VARIANT == 4 && iters) {
+        full_wait(0);
+        const uint4 *k = reinterpret_cast<const uint4 *>(&S.kw[0][0][lane][0]);
+        n0 = k[0]; n1 = k[1]; n2 = k[2]; n3 = k[3]; n4 = k[4];
+    }
     for (uint64_t i = 0; i < iters; i++) {
         const uint32_t PID = (uint32_t)i & 1u, SLOT = (uint32_t)(i >> 1) & 1u;
-        { long long t0_ = dbg_out ? clock64() : 0; mf_bar_sync_r(MF_BAR_FULL(UNIT, PID, SLOT)); if (dbg_out) cwait += clock64() - t0_; }
+        if (VARIANT != 4) { long long t0_ = dbg_out ? clock64() : 0; mf_bar_sync_r(MF_BAR_FULL(UNIT, PID, SLOT)); if (dbg_out) cwait += clock64() - t0_; }
         const uint4 *kwv = reinterpret_cast<const uint4 *>(&S.kw[PID][SLOT][lane][0]);
         uint32_t a = h0, b = h1, c = h2, d = h3, e = h4;
         // (Measured: building T with two FMA-pipe IMADs instead of one ALU IADD3 is slower, 1040 vs 890
@@ -213,10 +240,32 @@ __device__ __forceinline__ void mf_sha_consume(MfShaSmem &S, const MfShaLane &L,
         MF_RND(F, a, b, c, d, e, k1.y) MF_RND(F, e, a, b, c, d, k1.z) MF_RND(F, d, e, a, b, c, k1.w) MF_RND(F, c, d, e, a, b, k2.x) MF_RND(F, b, c, d, e, a, k2.y) \
         MF_RND(F, a, b, c, d, e, k2.z) MF_RND(F, e, a, b, c, d, k2.w) MF_RND(F, d, e, a, b, c, k3.x) MF_RND(F, c, d, e, a, b, k3.y) MF_RND(F, b, c, d, e, a, k3.z) \
         MF_RND(F, a, b, c, d, e, k3.w) MF_RND(F, e, a, b, c, d, k4.x) MF_RND(F, d, e, a, b, c, k4.y) MF_RND(F, c, d, e, a, b, k4.z) MF_RND(F, b, c, d, e, a, k4.w) }
+#define MF_RND20K(F, k0, k1, k2, k3, k4) { \
+        MF_RND(F, a, b, c, d, e, k0.x) MF_RND(F, e, a, b, c, d, k0.y) MF_RND(F, d, e, a, b, c, k0.z) MF_RND(F, c, d, e, a, b, k0.w) MF_RND(F, b, c, d, e, a, k1.x) \
+        MF_RND(F, a, b, c, d, e, k1.y) MF_RND(F, e, a, b, c, d, k1.z) MF_RND(F, d, e, a, b, c, k1.w) MF_RND(F, c, d, e, a, b, k2.x) MF_RND(F, b, c, d, e, a, k2.y) \
+        MF_RND(F, a, b, c, d, e, k2.z) MF_RND(F, e, a, b, c, d, k2.w) MF_RND(F, d, e, a, b, c, k3.x) MF_RND(F, c, d, e, a, b, k3.y) MF_RND(F, b, c, d, e, a, k3.z) \
+        MF_RND(F, a, b, c, d, e, k3.w) MF_RND(F, e, a, b, c, d, k4.x) MF_RND(F, d, e, a, b, c, k4.y) MF_RND(F, c, d, e, a, b, k4.z) MF_RND(F, b, c, d, e, a, k4.w) }
+        if (VARIANT == 4) {
+            MF_RND20K(MF_F_CH, n0, n1, n2, n3, n4)
+            MF_RND20(MF_F_PAR, 1)
+            const bool more = i + 1 < iters;
+            void *nbar = &S.full[(i + 1) & 1u][((i + 1) >> 1) & 1u];
+            const uint32_t npar = (uint32_t)((i + 1) >> 2) & 1u;
+            const uint32_t ok = more ? mf_mbar_test(nbar, npar) : 1u;
+            MF_RND20(MF_F_MAJ, 2)
+            if (more) {
+                if (!ok) full_wait(i + 1);                  // (a successful test was the acquire: the loads below come after it)
+                const uint4 *k = reinterpret_cast<const uint4 *>(&S.kw[(i + 1) & 1u][((i + 1) >> 1) & 1u][lane][0]);
+                n0 = k[0]; n1 = k[1]; n2 = k[2]; n3 = k[3]; n4 = k[4];
+            }
+            MF_RND20(MF_F_PAR, 3)
+        } else {
         MF_RND20(MF_F_CH, 0)
         MF_RND20(MF_F_PAR, 1)
         MF_RND20(MF_F_MAJ, 2)
         MF_RND20(MF_F_PAR, 3)
+        }
+#undef MF_RND20K
 #undef MF_RND20
 #undef MF_RND
         if (i < nb) { h0 += a; h1 += b; h2 += c; h3 += d; h4 += e; }
@@ -251,6 +300,11 @@ __global__ void __launch_bounds__(MF_SHA_THREADS, 1) mf_sha1_kernel(const MfHash
     extern __shared__ __align__(16) uint8_t mf_sha_smem_raw[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     if (gate && threadIdx.x == 0) atomicAdd(gate, 1u);
+    if (VARIANT == 4) {
+        if (threadIdx.x < 8) mf_mbar_init(&reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw)[threadIdx.x >> 2].full[(threadIdx.x >> 1) & 1u][threadIdx.x & 1u], 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     if (warp == 4 || warp == 5) return;                      // keep the consumers' sub-partitions to themselves
     const uint32_t unit = warp & 1u;
     MfShaSmem &S = reinterpret_cast<MfShaSmem *>(mf_sha_smem_raw)[unit];
@@ -274,5 +328,5 @@ __global__ void __launch_bounds__(MF_SHA_THREADS, 1) mf_sha1_kernel(const MfHash
     L.iters = iters;
     unsigned long long *dbg_out = dbg ? dbg + ((size_t)blockIdx.x * MF_SHA_UNITS + unit) * 4 : nullptr;
     if (warp < 2) mf_sha_consume<VARIANT>(S, L, unit, desc, lane, digests, dbg_out, one, k30);
-    else mf_sha_produce(S, L, unit, warp < 4 ? 0u : 1u, lane, dbg_out);
+    else mf_sha_produce<VARIANT == 4>(S, L, unit, warp < 4 ? 0u : 1u, lane, dbg_out);
 }

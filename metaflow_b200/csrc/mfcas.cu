@@ -137,7 +137,7 @@ struct Carver {
 #define MF_SHA_DEFAULT_VARIANT 0
 #define MF_ENC_DEFAULT_CRC 0
 #define MF_DEC_DEFAULT_OCC 4
-#define MF_DEC_DEFAULT_CRC 0
+#define MF_DEC_DEFAULT_CRC 1
 #define MF_RING 8
 // Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
 // takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
@@ -167,7 +167,7 @@ int device_setup(DeviceState &D) {
     CU(cudaStreamCreateWithFlags(&D.compute, cudaStreamNonBlocking));
     D.ring.resize(MF_RING);
     for (auto &W : D.ring) { int rc = wave_setup(D, W); if (rc != MFCAS_OK) return rc; }
-    for (auto k : {mf_sha1_kernel<0>, mf_sha1_kernel<1>, mf_sha1_kernel<3>}) {
+    for (auto k : {mf_sha1_kernel<0>, mf_sha1_kernel<1>, mf_sha1_kernel<3>, mf_sha1_kernel<4>}) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_SHA_UNITS * sizeof(MfShaSmem))));
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
@@ -177,7 +177,11 @@ int device_setup(DeviceState &D) {
         CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     }
     for (auto k : {mf_inflate_chunk_kernel<5, 0>, mf_inflate_chunk_kernel<4, 0>, mf_inflate_chunk_kernel<4, 1>})
-        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MfDecSmem)));
+    {
+        static_assert(4u * (MF_DEC_SMEM_BYTES + 1024u) <= 228u * 1024u, "four decoder CTAs per SM must fit the B200's 228 KB of shared memory");
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MF_DEC_SMEM_BYTES));
+        CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CU(cudaFuncSetAttribute(mf_fsize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
     CU(cudaFuncSetAttribute(mf_fdecode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MF_F_LANES * sizeof(MfSpecLane))));
     // SHA-1 and the encoder share SMs (one 100+ KB CTA each).  An SM cannot hold CTAs of kernels whose L1/shared
@@ -448,7 +452,7 @@ int pack_submit(DeviceState &D, WaveCtx &W, uint32_t flags, uint64_t n, const vo
     W.sha_ctas = sha_ctas;
     {
         static const int variant = getenv("MFCAS_SHA_VARIANT") ? atoi(getenv("MFCAS_SHA_VARIANT")) : MF_SHA_DEFAULT_VARIANT;
-        auto kern = variant == 1 ? mf_sha1_kernel<1> : variant == 3 ? mf_sha1_kernel<3> : mf_sha1_kernel<0>;
+        auto kern = variant == 1 ? mf_sha1_kernel<1> : variant == 3 ? mf_sha1_kernel<3> : variant == 4 ? mf_sha1_kernel<4> : mf_sha1_kernel<0>;
         kern<<<sha_ctas, MF_SHA_THREADS, sha_smem, s2>>>(reinterpret_cast<const MfHashDesc *>(dd + o_hash), (uint32_t)n, dres + W.r_sha, sha_dbg, gate, 1u, 1u << 30);
     }
     CU(cudaGetLastError());
@@ -670,8 +674,12 @@ int unpack_submit(DeviceState &D, WaveCtx &W, uint64_t n, const void *const *d_s
     static const int dec_occ = getenv("MFCAS_DEC_OCC") ? atoi(getenv("MFCAS_DEC_OCC")) : MF_DEC_DEFAULT_OCC;
     static const int dec_crc = getenv("MFCAS_DEC_CRC") ? atoi(getenv("MFCAS_DEC_CRC")) : MF_DEC_DEFAULT_CRC;
     auto dec_kernel = dec_occ == 5 ? mf_inflate_chunk_kernel<5, 0> : (dec_crc ? mf_inflate_chunk_kernel<4, 1> : mf_inflate_chunk_kernel<4, 0>);
-    dec_kernel<<<(unsigned)((max_chunks + MF_DEC_WARPS * MF_DEC_GROUP - 1) / (MF_DEC_WARPS * MF_DEC_GROUP)), 32 * MF_DEC_WARPS, sizeof(MfDecSmem), s>>>(
-        reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st));
+    static const unsigned dec_group = getenv("MFCAS_DEC_GROUP") ? (unsigned)std::max(1, atoi(getenv("MFCAS_DEC_GROUP"))) : MF_DEC_GROUP;
+    // resident warps take groups of chunks by ticket: a grid that fills the SMs once (B200: 148 SMs), or less for a small call
+    const unsigned dec_grid = (unsigned)std::min<uint64_t>((max_chunks + (uint64_t)MF_DEC_WARPS * dec_group - 1) / ((uint64_t)MF_DEC_WARPS * dec_group),
+                                                         148ull * (dec_occ == 5 ? 5u : 4u));
+    dec_kernel<<<std::max(dec_grid, 1u), 32 * MF_DEC_WARPS, MF_DEC_SMEM_BYTES, s>>>(
+        reinterpret_cast<const MfDecChunk *>(dw + o_chunks), cnt, reinterpret_cast<uint32_t *>(dw + o_crc), reinterpret_cast<int32_t *>(dres + W.r_st), dec_group);
     CU(cudaGetLastError());
     CU(cudaEventRecord(W.ev[6], s));
     mf_verify_kernel<<<(unsigned)((max_members * 32 + 127) / 128), 128, 0, s>>>(

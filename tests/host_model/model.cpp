@@ -310,4 +310,34 @@ int model_gunzip_parallel(const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t
     return 0;
 }
 
+// ---- the chunk decoder's quick block-header parser against the portable one (both from mf_inflate_core.h)
+struct HostWordReader {
+    const uint8_t *p; uint64_t n, pos; uint64_t buf; uint32_t cnt, fetched;
+    uint32_t word() { uint32_t v = 0; for (int k = 0; k < 4; k++) if (pos + k < n) v |= (uint32_t)p[pos + k] << (8 * k); pos += 4; return v; }
+    void init(const uint8_t *src, uint64_t nbytes) { p = src; n = nbytes; pos = 0; buf = word(); buf |= (uint64_t)word() << 32; cnt = 64; fetched = 64; }
+    void fill() { if (cnt <= 32u) { buf |= (uint64_t)word() << cnt; cnt += 32u; fetched += 32u; } }
+    uint32_t peek(uint32_t k) { return (uint32_t)buf & ((1u << k) - 1u); }
+    void drop(uint32_t k) { buf >>= k; cnt -= k; }
+    uint32_t get(uint32_t k) { uint32_t v = peek(k); drop(k); return v; }
+    uint32_t used() const { return fetched - cnt; }
+};
+
+// out[0..2] = fast: bits (0 = declined), hlit, hdist; out[3..6] = portable: error, bits, hlit, hdist.
+// `n` bytes are readable (the blob), the chunk is the first comp_bytes of them.
+void model_header_both(const uint8_t *src, uint64_t n, uint32_t comp_bytes, uint8_t *lens_fast, uint8_t *lens_port, uint32_t *out) {
+    uint8_t cl_lut[128];
+    memset(cl_lut, 0, sizeof cl_lut);
+    uint32_t hl = 0, hd = 0;
+    HostWordReader wr; wr.init(src, n);
+    out[0] = mf_read_header_fast_t(wr, comp_bytes, lens_fast, cl_lut, hl, hd);
+    out[1] = hl; out[2] = hd;
+    MfBitReader br; br.init(src, comp_bytes, 0);
+    uint32_t bfinal = br.get(1), btype = br.get(2);
+    int e = 0;
+    hl = hd = 0;
+    if (bfinal != 0 || btype != 2) e = MF_DEC_E_STREAM;
+    if (!e) e = mf_read_dynamic_tables(br, lens_port, hl, hd);
+    out[3] = (uint32_t)e; out[4] = e ? 0u : (uint32_t)br.bitpos(); out[5] = hl; out[6] = hd;
+}
+
 }  // extern "C"

@@ -27,6 +27,8 @@ def lib():
     L.model_gunzip.argtypes = sig
     L.model_unpack_indexed.argtypes = sig
     L.model_gunzip_parallel.argtypes = sig + [ctypes.POINTER(ctypes.c_uint64)]
+    L.model_header_both.restype = None
+    L.model_header_both.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     _lib = L
     return L
 
@@ -62,3 +64,16 @@ def gunzip_parallel(z, cap):
     stats = (ctypes.c_uint64 * 3)()
     e = lib().model_gunzip_parallel(z, len(z), out, cap, ctypes.byref(p), stats)
     return e, out.raw[: p.value] if e == 0 else b"", tuple(stats)
+
+
+def header_both(src, comp_bytes=None):
+    """Block header at the start of `src` through the quick parser and the portable one:
+    -> ((bits, hlit, hdist, lens) or None when the quick parser declines, (error, bits, hlit, hdist, lens))."""
+    L = lib()
+    comp = len(src) if comp_bytes is None else comp_bytes
+    lf, lp = ctypes.create_string_buffer(320), ctypes.create_string_buffer(320)
+    out = (ctypes.c_uint32 * 7)()
+    L.model_header_both(bytes(src), len(src), comp, lf, lp, out)
+    fast = None if out[0] == 0 else (out[0], out[1], out[2], lf.raw[: out[1] + out[2]])
+    port = (out[3], out[4], out[5], out[6], lp.raw[: out[5] + out[6]] if out[3] == 0 else b"")
+    return fast, port

@@ -167,3 +167,61 @@ def test_block_parallel_foreign_decoder_model():
     assert model_lib.gunzip_parallel(bytes(z[: len(z) // 2]), len(cases["normal_big"]))[0] != 0
     e, _, _ = model_lib.gunzip_parallel(bytes(z), len(cases["normal_big"]) - 1)
     assert e == 1
+
+
+def test_fast_header_parser_equals_the_portable_one():
+    """mf_read_header_fast_t (7-bit table for the code-length code, word reader) either declines (0) or returns exactly what
+    mf_read_dynamic_tables returns: on zlib's headers, on ours (where the bit count must equal the index entry), and on
+    mutated / random headers."""
+    rng = np.random.default_rng(77)
+
+    def check(buf, comp=None, want_bits=None):
+        fast, port = model_lib.header_both(buf, comp)
+        if fast is None:
+            assert want_bits is None, "the quick parser declined a good header"
+            return False
+        assert port[0] == 0, (fast[:3], port[:4])
+        assert fast[0] == port[1] and fast[1] == port[2] and fast[2] == port[3] and fast[3] == port[4]
+        if want_bits is not None:
+            assert fast[0] == want_bits
+        return True
+
+    samples = [rng.standard_normal(50000, dtype=np.float32).tobytes(), rng.integers(0, 4, 200000, dtype=np.uint8).tobytes(),
+               (b"the quick brown fox jumps over the lazy dog %d " * 4000) % tuple(range(4000)), bytes(rng.integers(0, 256, 150000, dtype=np.uint8)),
+               np.arange(60000, dtype=np.int32).tobytes(), rng.integers(0, 256, 100000, dtype=np.uint8).repeat(3).tobytes()]
+    headers, accepted = [], 0
+    for data in samples:
+        for level in (1, 3, 6, 9):
+            co = zlib.compressobj(level, zlib.DEFLATED, -15)
+            z = co.compress(data) + co.flush()
+            if (z[0] & 7) == 4:                                  # BFINAL 0, BTYPE 10
+                accepted += check(z)
+                headers.append(z[:400])
+        z = model_lib.pack(data)
+        raw_len, nc = int.from_bytes(z[20:24], "little"), int.from_bytes(z[24:28], "little")
+        off = 32 + 72 * nc
+        for c in range(nc):
+            comp = int.from_bytes(z[32 + 8 * c:36 + 8 * c], "little")
+            bits = int.from_bytes(z[36 + 8 * c:38 + 8 * c], "little")
+            if bits != 0xFFFF:                                   # not a stored chunk
+                accepted += check(z[off:], comp, bits)
+                headers.append(z[off:off + 400])
+            off += comp
+    assert accepted >= 40 and len(headers) >= 40
+    # a header cut short: the chunk ends inside it
+    for h in headers[:8]:
+        fast, port = model_lib.header_both(h, 20)
+        assert fast is None and port[0] != 0
+    # mutations: single bit flips in the first 100 bytes, and random tails behind a valid first byte
+    flips = 0
+    for h in headers:
+        for _ in range(60):
+            m = bytearray(h)
+            bit = int(rng.integers(0, 800))
+            m[bit >> 3] ^= 1 << (bit & 7)
+            flips += check(bytes(m))
+    for _ in range(3000):
+        m = bytearray(rng.integers(0, 256, 300, dtype=np.uint8).tobytes())
+        m[0] = (m[0] & 0xF8) | 4
+        check(bytes(m))
+    assert flips > 100          # many mutated headers are still well-formed: the comparison above really ran

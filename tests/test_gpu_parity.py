@@ -448,3 +448,53 @@ def test_client_filecache_batched_fetch_on_gpu(gpu_codec, tmp_path):
     assert gpu_codec.counters()["kernel_launches"] == l1             # all from the cache files
     assert np.array_equal(again[("3", "train", "7")]["weights"], arrays[7])
     assert np.array_equal(fc.get_artifact("local", str(tmp_path / "ds"), None, "ClientFlow", "3", "train", "5", "weights"), arrays[5])
+
+
+def test_device_resident_extents_and_in_place_compaction(gpu_codec):
+    """mfcas_pack_device_extents (members written straight into fixed slots of the destination) + mfcas_compact_device (moved
+    together in place) = the contiguous RFC 1952 file mfcas_unpack_device takes; undersized destinations are reported per blob."""
+    import torch
+    from metaflow_b200 import capi
+    lib = capi.load()
+    rng = np.random.default_rng(19)
+    blobs = [rng.standard_normal(1400000, dtype=np.float32).tobytes(), b"", rng.integers(0, 7, 2097152 + 5, dtype=np.uint8).tobytes(),
+             b"short", rng.standard_normal(300, dtype=np.float32).tobytes()]
+    n = len(blobs)
+    u64, vp = ctypes.c_uint64, ctypes.c_void_p
+    d_src = [torch.frombuffer(bytearray(b) + bytearray(16), dtype=torch.uint8).cuda() for b in blobs]
+    caps = [lib.mfcas_pack_extent_bound(len(b)) for b in blobs]
+    cnt = [lib.mfcas_pack_extent_count(len(b)) for b in blobs]
+    caps[3] = 8                                                     # blob 3 cannot fit
+    d_dst = [torch.zeros(max(c, 64) + 256, dtype=torch.uint8, device="cuda") for c in caps]
+    torch.cuda.synchronize()
+    src = (vp * n)(*[t.data_ptr() for t in d_src]); dst = (vp * n)(*[t.data_ptr() for t in d_dst])
+    slen = (u64 * n)(*map(len, blobs)); cap = (u64 * n)(*caps)
+    eo = (u64 * sum(cnt))(); el = (u64 * sum(cnt))(); st = (ctypes.c_int32 * n)(); sha = ctypes.create_string_buffer(20 * n)
+    assert lib.mfcas_pack_device_extents(gpu_codec._ctx, 0, n, src, slen, dst, cap, eo, el, sha, st) == 0
+    assert list(st) == [0, 0, 0, capi.E_DST_TOO_SMALL, 0]
+    for i, b in enumerate(blobs):
+        assert sha.raw[20 * i:20 * i + 20] == hashlib.sha1(b).digest()
+    assert cnt == [3, 1, 2, 1, 1]
+    dlen = (u64 * n)()
+    assert lib.mfcas_compact_device(gpu_codec._ctx, 0, n, dst, slen, el, dlen) == 0
+    base = 0
+    for i, b in enumerate(blobs):
+        if st[i] == 0:
+            assert dlen[i] == sum(el[base + k] for k in range(cnt[i]))
+            z = d_dst[i][: dlen[i]].cpu().numpy().tobytes()
+            assert gzip.decompress(z) == b
+            e, out = c_oracle.gunzip(z, len(b))
+            assert e == 0 and out == b
+        base += cnt[i]
+    # and back through the device decoder
+    good = [0, 1, 2, 4]
+    m = len(good)
+    d_out = [torch.zeros(len(blobs[i]) + 16, dtype=torch.uint8, device="cuda") for i in good]
+    torch.cuda.synchronize()
+    psrc = (vp * m)(*[d_dst[i].data_ptr() for i in good]); plen = (u64 * m)(*[dlen[i] for i in good])
+    out = (vp * m)(*[t.data_ptr() for t in d_out]); ocap = (u64 * m)(*[len(blobs[i]) for i in good])
+    olen = (u64 * m)(); st2 = (ctypes.c_int32 * m)()
+    assert lib.mfcas_unpack_device(gpu_codec._ctx, 0, m, psrc, plen, out, ocap, olen, st2) == 0
+    assert list(st2) == [0] * m
+    for k, i in enumerate(good):
+        assert d_out[k][: len(blobs[i])].cpu().numpy().tobytes() == blobs[i]
