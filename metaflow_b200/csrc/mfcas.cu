@@ -137,7 +137,7 @@ struct Carver {
 #define MF_SHA_DEFAULT_VARIANT 0
 #define MF_ENC_DEFAULT_CRC 0
 #define MF_DEC_DEFAULT_OCC 4
-#define MF_DEC_DEFAULT_CRC 1
+#define MF_DEC_DEFAULT_CRC 0
 #define MF_RING 8
 // Encoder CTAs resident at once: two per SM, on the SMs that the SHA-1 CTAs in flight do not own (a SHA-1 CTA
 // takes a whole SM: 216 KB of shared memory).  The persistent encoder grid is sized to leave those SMs free;
