@@ -171,6 +171,11 @@ struct __align__(16) MfDecSmem {
 // Per-lane output writer: decoded bytes go straight to the lane's 1 KiB segment in HBM, 16 bytes at a
 // time from registers; the raw CRC-32 (slice-by-4) is folded in as every 4-byte word completes.  No
 // shared-memory staging of the output: what limits resident decoder lanes is registers, not smem.
+// 16 bytes of output (the destination is global memory: say so, the pointer comes out of a descriptor and would be a generic ST)
+__device__ __forceinline__ void mf_store16(uint8_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 struct MfLaneWriter {
     uint8_t *dst;        // segment base in global memory
     uint32_t op;         // bytes produced
@@ -191,7 +196,7 @@ struct MfLaneWriter {
 #pragma unroll
             for (int k = 0; k < 4; k++) w[k] |= cw & (0u - (uint32_t)(j == (uint32_t)k));    // branch-free: w[] stays in registers
             if ((op & 15u) == 0) {
-                *reinterpret_cast<uint4 *>(dst + op - 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                mf_store16(dst + op - 16, w[0], w[1], w[2], w[3]);
                 w[0] = w[1] = w[2] = w[3] = 0;
             }
         } else if ((op & 15u) == 0 && aligned) vec = true;                    // realigned: back to window mode
@@ -384,6 +389,27 @@ __device__ __noinline__ uint32_t mf_read_header_fast(const uint8_t *src, uint32_
     return mf_read_header_fast_t(br, comp_bytes, lens, cl_lut, hlit_out, hdist_out);
 }
 
+// A code longer than the first-level table, out of line: the chunk decoder's unrolled path holds 16 copies of its lookup, and
+// with the 15-step canonical walk inlined behind each of them the loop was 160 KB of code that the hot path hops through
+// (ncu: `no_instruction` 1.7 stalled warps per issue).  Returns symbol | length << 16, or 0xFFFFFFFF when no code matches.
+__device__ __noinline__ uint32_t mf_canon_decode_cold(uint32_t bits, const uint16_t *count, const uint16_t *symbol) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; l++) {
+        code |= (int)(bits & 1u); bits >>= 1;
+        int cnt = count[l];
+        if (code - cnt < first) return (uint32_t)symbol[index + (code - first)] | ((uint32_t)l << 16);
+        index += cnt; first += cnt; first <<= 1; code <<= 1;
+    }
+    return 0xFFFFFFFFu;
+}
+template <typename Reader>
+__device__ __forceinline__ int mf_canon_decode_call(Reader &br, const uint16_t *count, const uint16_t *symbol) {
+    const uint32_t r = mf_canon_decode_cold((uint32_t)br.buf, count, symbol);
+    if (r == 0xFFFFFFFFu) return -1;
+    br.drop(r >> 16);
+    return (int)(r & 0xFFFFu);
+}
+
 template <int MINB, int DCRC>
 __global__ void __launch_bounds__(32 * MF_DEC_WARPS, MINB)   // 5: 48 registers, 40 warps per SM (round 1: 3: 102 ms, 4: 81 ms, 5: 78 ms, 6: 99 ms per 34 GB)
 mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__restrict__ counters,
@@ -565,7 +591,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__
                             } else {
                                 int s2;
                                 if (e != MF_LL_MISS) { s2 = 256 + (int)(e & 0xFFu); br.drop((e >> 8) & 0x7Fu); }
-                                else s2 = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol);
+                                else s2 = mf_canon_decode_call(br, W.ll.count, W.ll.symbol);
                                 if ((uint32_t)s2 >= 256u) { sym = s2; wr.op = op0 + (uint32_t)k; break; }   // a length / end-of-block symbol, or -1
                                 wr.cw |= (uint32_t)s2 << (8 * (k & 3));             // a literal with a code longer than the table
                             }
@@ -579,7 +605,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__
                         }
                         if (sym == -2) {       // all 16 were literals
                             wr.op = op0 + 16u;
-                            *reinterpret_cast<uint4 *>(wr.dst + op0) = make_uint4(wr.w[0], wr.w[1], wr.w[2], wr.w[3]);
+                            mf_store16(wr.dst + op0, wr.w[0], wr.w[1], wr.w[2], wr.w[3]);
                             wr.w[0] = wr.w[1] = wr.w[2] = wr.w[3] = 0;
                             continue;
                         }
@@ -588,7 +614,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__
                         br.fill();
                         const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
                         if (e != MF_LL_MISS) { sym = (int)((e & 0xFFu) + ((e >> 15) << 8)); br.drop((e >> 8) & 0x7Fu); }
-                        else { sym = mf_canon_decode_fast(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
+                        else { sym = mf_canon_decode_call(br, W.ll.count, W.ll.symbol); if (sym < 0) { lerr = MF_DEC_E_STREAM; break; } }
                         if (sym < 256) { wr.put((uint32_t)sym, S.crc_tab); continue; }
                     }
                     if (sym == 256 || sym > 285) { lerr = MF_DEC_E_STREAM; break; }
@@ -599,7 +625,7 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__
                     uint32_t de = W.lut_d[br.peek(MF_D_LUT_BITS)];
                     int ds;
                     if (de) { ds = (int)(de & 31u); br.drop(de >> 5); }
-                    else { ds = mf_canon_decode_fast(br, W.dd.count, W.dd.symbol); if (ds < 0) { lerr = MF_DEC_E_STREAM; break; } }
+                    else { ds = mf_canon_decode_call(br, W.dd.count, W.dd.symbol); if (ds < 0) { lerr = MF_DEC_E_STREAM; break; } }
                     if (ds >= 30) { lerr = MF_DEC_E_STREAM; break; }
                     br.fill();
                     uint32_t dist = mf_dbase(ds) + br.get(mf_dext(ds));
