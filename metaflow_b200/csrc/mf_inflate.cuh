@@ -584,10 +584,12 @@ mf_inflate_chunk_kernel(const MfDecChunk *__restrict__ chunks, MfDecCounters *__
                         for (int k = 0; k < 16; k++) {
                             if (k && (k & 3) == 0) br.refill();   // refill point every 4 literals (<= 60 bits)
                             if ((k & 1) == 0) br.fill();          // > 32 bits in the buffer: enough for two symbols of <= 15 bits
-                            const uint32_t e = W.lut_ll[br.peek(MF_LL_LUT_BITS)];
-                            if (e < MF_LL_MISS) {                                   // a literal: drop its bits, put its byte in place
-                                br.drop(e >> 8);
-                                wr.cw = __byte_perm(wr.cw, e, (k & 3) == 0 ? 0x3214u : ((k & 3) == 1 ? 0x3240u : ((k & 3) == 2 ? 0x3410u : 0x4210u)));
+                            // (read as a SIGNED 16-bit value: the load sign-extends, and `>= 0` is the literal test)
+                            const int es = (int)reinterpret_cast<const int16_t *>(W.lut_ll)[br.peek(MF_LL_LUT_BITS)];
+                            const uint32_t e = (uint32_t)es & 0xFFFFu;
+                            if (__builtin_expect(es >= 0, 1)) {                     // a literal: drop its bits, put its byte in place
+                                br.drop((uint32_t)es >> 8);
+                                wr.cw = __byte_perm(wr.cw, (uint32_t)es, (k & 3) == 0 ? 0x3214u : ((k & 3) == 1 ? 0x3240u : ((k & 3) == 2 ? 0x3410u : 0x4210u)));
                             } else {
                                 int s2;
                                 if (e != MF_LL_MISS) { s2 = 256 + (int)(e & 0xFFu); br.drop((e >> 8) & 0x7Fu); }
