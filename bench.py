@@ -527,8 +527,10 @@ def run_ours(args, rank, world, local_rank):
         if os.path.exists(tpath):
             with open(tpath) as f:
                 tj = json.load(f)
-            per_blob = tj.get("per_blob", {}).get(names[dominant])     # measured with ncu on tj["blobs"] blobs of this size; linear in blobs
-            traffic = per_blob * n if per_blob else None
+            # measured with ncu on tj["blobs"] blobs of tj["blob_bytes"] bytes; every kernel streams each byte once, so the
+            # traffic of a launch is linear in the raw bytes it processes (whatever the blob size)
+            per_byte = tj.get("per_raw_byte", {}).get(names[dominant])
+            traffic = per_byte * n * blob_len if per_byte else None
         cpu = None
         if not args.no_cpu_baseline:
             cores = usable_cores()
