@@ -118,7 +118,10 @@ int mfcas_unpack_batch(mfcas_ctx *ctx, uint64_t n,
 /* Device-resident variants (src/dst are DEVICE pointers on context device slot `dev_slot`,
  * src 16-byte aligned; dst_len/sha1/status are HOST arrays filled before return).  Used by
  * bench.py for the HBM-resident roofline measurement and by callers that keep artifacts on
- * the GPU.  The work is enqueued on mfcas_stream(ctx, dev_slot) and the call synchronises it. */
+ * the GPU.  The work is enqueued on mfcas_stream(ctx, dev_slot) and the call synchronises it.
+ * mfcas_unpack_device reads its sources in whole 16-byte quads: d_src[i] must be readable up to the
+ * next 16-byte boundary behind d_src[i] + src_len[i] (true of any buffer that ends where a device
+ * allocation ends, and of sub-buffers with 15 bytes of slack; the host-path arenas leave 256). */
 int mfcas_pack_device(mfcas_ctx *ctx, int dev_slot, uint64_t n,
                       const void *const *d_src, const uint64_t *src_len,
                       void *const *d_dst, const uint64_t *dst_cap, uint64_t *dst_len,
