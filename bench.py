@@ -447,7 +447,9 @@ def run_ours(args, rank, world, local_rank):
     # tmpfs), timed between barriers, aggregated like the other legs (all ranks' bytes / slowest rank's time)
     api = None
     api_t = [0.0, 0.0]
-    api_blobs = min(args.api_blobs, n)
+    # the object-level sample is sized per JOB (1024 artifacts = 17 GB in total at the default), not per rank: its host memory
+    # (arrays, files on tmpfs, decoded copies) must not grow with the GPU count
+    api_blobs = min(max(args.api_blobs // world, min(args.api_blobs, 64)), n)
     del d_packed, d_out                                   # the object-level leg brings its own context and arenas
     torch.cuda.empty_cache()
     if api_blobs > 0:
@@ -585,7 +587,7 @@ def main():
     ap.add_argument("--wave-mib", type=int, default=1024, help="bytes (in+out) per pipelined wave of the host-pointer API")
     ap.add_argument("--ref-blobs-per-proc", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--api-blobs", type=int, default=1024, help="artifacts per rank in the L-api (objects <-> tmpfs files) leg; 0 = skip")
+    ap.add_argument("--api-blobs", type=int, default=1024, help="artifacts of the whole job in the L-api (objects <-> tmpfs files) leg, split over the ranks (at least 64 each); 0 = skip")
     args = ap.parse_args()
     global ARRAY_ELEMS
     ARRAY_ELEMS = CONFIGS[args.config][0]
