@@ -42,16 +42,17 @@ def pack_sharded(codec, blobs, rank=0, world=1, all_gather=None):
 # ------------------------------------------------------------------------------------------------------
 # The multi-process batcher: ONE process per box owns the GPU context(s); task processes -- the children
 # multicore_utils.parallel_map forks, or stock one-process-per-task runs (metaflow/runtime.py:1517-1577,
-# 2287-2350) pointed at a running daemon -- hand their blobs over through files in shared memory
-# (/dev/shm) and small messages on a Unix socket.  Requests that arrive while a GPU batch is running are
+# 2287-2350) pointed at a running daemon -- hand their blobs over in anonymous shared memory (memfd; the
+# DESCRIPTOR travels with the message, SCM_RIGHTS: no names in /dev/shm, nothing to leak when a client dies)
+# and small JSON messages on a Unix socket only its owner can connect to.  Requests that arrive while a GPU batch is running are
 # merged into the next one, so N concurrently saving tasks become one wide batch (a SHA-1 lane does
 # ~150 MB/s; width is what makes the GPU path fast), sharded round-robin over the GPUs by libmfcas.
 #
 #   server:  CodecServer(codec).start()        or   python -m metaflow_b200.batcher serve [--socket PATH]
 #   client:  METAFLOW_GPU_CAS_SERVER=<socket path>  ->  codec.default_codec() returns a RemoteCodec
+import json
 import mmap
 import os
-import pickle
 import queue
 import socket
 import struct
@@ -60,11 +61,20 @@ import threading
 
 SERVER_ENV = "METAFLOW_GPU_CAS_SERVER"
 _SHM_DIR = "/dev/shm" if os.path.isdir("/dev/shm") else None
+_MAX_MSG = 256 << 20          # a message is lengths and keys, never payload
 
 
-def _send_msg(sock, obj):
-    data = pickle.dumps(obj, protocol=4)
-    sock.sendall(struct.pack("<Q", len(data)) + data)
+def _send_msg(sock, obj, fds=()):
+    """One message: 8-byte length (descriptors ride on it), then JSON.  Nothing that crosses the socket is unpickled."""
+    data = json.dumps(obj).encode("utf-8")
+    hdr = struct.pack("<Q", len(data))
+    if fds:
+        sent = socket.send_fds(sock, [hdr], list(fds))
+        if sent < len(hdr):
+            sock.sendall(hdr[sent:])
+    else:
+        sock.sendall(hdr)
+    sock.sendall(data)
 
 
 def _recv_exact(sock, n):
@@ -78,8 +88,23 @@ def _recv_exact(sock, n):
 
 
 def _recv_msg(sock):
-    (n,) = struct.unpack("<Q", _recv_exact(sock, 8))
-    return pickle.loads(_recv_exact(sock, n))
+    """-> (message, [descriptors that came with it]); the caller owns the descriptors."""
+    head, fds, _flags, _addr = socket.recv_fds(sock, 8, 4)
+    if not head:
+        for fd in fds:
+            os.close(fd)
+        raise EOFError("peer closed the batcher socket")
+    try:
+        if len(head) < 8:
+            head += _recv_exact(sock, 8 - len(head))
+        (n,) = struct.unpack("<Q", head)
+        if n > _MAX_MSG:
+            raise ValueError("batcher message of %d bytes" % n)
+        return json.loads(_recv_exact(sock, n).decode("utf-8")), list(fds)
+    except Exception:
+        for fd in fds:
+            os.close(fd)
+        raise
 
 
 def _layout(lens):
@@ -92,34 +117,39 @@ def _layout(lens):
 
 
 class _Segment(object):
-    """A file in shared memory holding a list of byte strings; the path is what crosses the socket."""
+    """Anonymous shared memory holding a list of byte strings back to back; its descriptor is what crosses the socket."""
 
-    def __init__(self, path, size, create):
-        self.path, self.size = path, size
-        flags = os.O_RDWR | (os.O_CREAT | os.O_EXCL if create else 0)
-        fd = os.open(path, flags, 0o600)
+    def __init__(self, fd, size):
+        self.fd, self.size = fd, size
         try:
-            if create:
-                os.ftruncate(fd, max(size, 1))
             self.map = mmap.mmap(fd, max(size, 1))
-        finally:
+        except Exception:
             os.close(fd)
+            self.fd = -1
+            raise
         self.view = memoryview(self.map)
 
     @classmethod
-    def create(cls, size, dir=None):
-        fd, path = tempfile.mkstemp(prefix="mfcas_seg_", dir=dir or _SHM_DIR)
-        os.close(fd)
-        os.unlink(path)
-        return cls(path, size, True)
-
-    def unlink(self):
+    def create(cls, size):
+        if hasattr(os, "memfd_create"):
+            fd = os.memfd_create("mfcas_seg", getattr(os, "MFD_CLOEXEC", 0))
+        else:                                   # no memfd: an unlinked file in shared memory is the same thing
+            fd, path = tempfile.mkstemp(prefix="mfcas_seg_", dir=_SHM_DIR)
+            os.unlink(path)
         try:
-            os.unlink(self.path)
-        except OSError:
-            pass
+            os.ftruncate(fd, max(size, 1))
+        except Exception:
+            os.close(fd)
+            raise
+        return cls(fd, size)
+
+    def close_fd(self):
+        if self.fd >= 0:
+            os.close(self.fd)
+            self.fd = -1
 
     def close(self):
+        self.close_fd()
         try:
             self.view.release()
             self.map.close()
@@ -128,12 +158,12 @@ class _Segment(object):
 
 
 class _Request(object):
-    __slots__ = ("op", "items", "reply", "done", "result", "error")
+    __slots__ = ("op", "items", "done", "result", "segment", "error")
 
     def __init__(self, op, items):
         self.op, self.items = op, items
         self.done = threading.Event()
-        self.result = self.error = None
+        self.result = self.segment = self.error = None
 
 
 class CodecServer(object):
@@ -160,7 +190,12 @@ class CodecServer(object):
         if os.path.exists(self.socket_path):
             os.unlink(self.socket_path)
         s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        s.bind(self.socket_path)
+        old_umask = os.umask(0o177)              # the socket is the access control: owner only
+        try:
+            s.bind(self.socket_path)
+        finally:
+            os.umask(old_umask)
+        os.chmod(self.socket_path, 0o600)
         s.listen(256)
         s.settimeout(0.2)
         self._sock = s
@@ -203,36 +238,44 @@ class CodecServer(object):
         with conn:
             while not self._stop.is_set():
                 try:
-                    msg = _recv_msg(conn)
-                except (EOFError, OSError):
+                    msg, fds = _recv_msg(conn)
+                except (EOFError, OSError, ValueError):
                     return
-                seg = None
+                seg = out_seg = None
                 try:
                     op = msg["op"]
                     if op == "ping":
                         _send_msg(conn, {"ok": True, "pid": os.getpid()})
                         continue
                     items = []
-                    if msg.get("segment"):
-                        seg = _Segment(msg["segment"], msg["size"], False)
-                        offs, _ = _layout(msg["lens"])
-                        items = [seg.view[o:o + ln] for o, ln in zip(offs, msg["lens"])]
+                    if msg.get("size") is not None and fds:
+                        seg = _Segment(fds.pop(0), int(msg["size"]))
+                        lens = [int(x) for x in msg["lens"]]
+                        offs, total = _layout(lens)
+                        if total > seg.size:
+                            raise ValueError("segment of %d bytes for %d bytes of blobs" % (seg.size, total))
+                        items = [seg.view[o:o + ln] for o, ln in zip(offs, lens)]
                     # unpack requests may name files instead: the server reads them straight into pinned memory
-                    for k, path in sorted(msg.get("files", {}).items()):
+                    for k, path in sorted((int(k), v) for k, v in msg.get("files", {}).items()):
                         items.insert(k, self._file_source(path))
                     req = _Request(op, items)
                     self._q.put(req)
                     req.done.wait()
+                    out_seg = req.segment
                     if req.error is not None:
                         _send_msg(conn, {"ok": False, "error": req.error})
                     else:
-                        _send_msg(conn, req.result)
-                except (OSError, KeyError, ValueError) as e:
+                        _send_msg(conn, req.result, [out_seg.fd] if out_seg is not None else ())
+                except (OSError, KeyError, ValueError, TypeError) as e:
                     try:
                         _send_msg(conn, {"ok": False, "error": "%s: %s" % (type(e).__name__, e)})
                     except OSError:
                         return
                 finally:
+                    for fd in fds:                   # descriptors the message did not account for
+                        os.close(fd)
+                    if out_seg is not None:          # the client has its own descriptor now (or is gone): ours can go
+                        out_seg.close()
                     if seg is not None:
                         items = None
                         seg.close()
@@ -289,7 +332,8 @@ class CodecServer(object):
                 pos = 0
                 for r in batch:
                     mine = packed[pos:pos + len(r.items)]
-                    r.result = dict(self._export([getattr(p, "views", [p]) for p in mine]), ok=True, keys=keys[pos:pos + len(r.items)])
+                    meta, r.segment = self._export([getattr(p, "views", [p]) for p in mine])
+                    r.result = dict(meta, ok=True, keys=keys[pos:pos + len(r.items)])
                     pos += len(r.items)
             elif op == "unpack":
                 out = self.codec.unpack_batch(flat, as_bytes=False) if flat else []
@@ -297,30 +341,37 @@ class CodecServer(object):
                 pos = 0
                 for r in batch:
                     mine = out[pos:pos + len(r.items)]
-                    errors = {i: (getattr(o, "code", -1), str(o)) for i, o in enumerate(mine) if isinstance(o, Exception)}
-                    r.result = dict(self._export([[o] if not isinstance(o, Exception) else [] for o in mine]), ok=True, errors=errors)
+                    errors = {str(i): [getattr(o, "code", -1), str(o)] for i, o in enumerate(mine) if isinstance(o, Exception)}
+                    meta, r.segment = self._export([[o] if not isinstance(o, Exception) else [] for o in mine])
+                    r.result = dict(meta, ok=True, errors=errors)
                     pos += len(r.items)
             else:
                 raise ValueError("unknown op %r" % (op,))
         except Exception as e:  # noqa: BLE001 -- a failed batch is reported to every client that was part of it
             for r in batch:
-                r.result, r.error = None, "%s: %s" % (type(e).__name__, e)
+                if r.segment is not None:
+                    r.segment.close()
+                r.result, r.segment, r.error = None, None, "%s: %s" % (type(e).__name__, e)
         for r in batch:
             r.done.set()
 
     @staticmethod
     def _export(pieces_per_blob):
-        """[[bytes-like piece, ...] per blob] -> a result segment: every blob's pieces joined, back to back."""
+        """[[bytes-like piece, ...] per blob] -> (message fields, result segment): every blob's pieces joined, back to back.
+        The segment's descriptor goes out with the reply; the caller closes the segment afterwards."""
         lens = [sum(len(p) for p in pieces) for pieces in pieces_per_blob]
         offs, total = _layout(lens)
         seg = _Segment.create(total)
-        for o, pieces in zip(offs, pieces_per_blob):
-            cur = o
-            for p in pieces:
-                seg.view[cur:cur + len(p)] = p
-                cur += len(p)
-        seg.close()
-        return {"segment": seg.path, "size": total, "lens": lens}
+        try:
+            for o, pieces in zip(offs, pieces_per_blob):
+                cur = o
+                for p in pieces:
+                    seg.view[cur:cur + len(p)] = p
+                    cur += len(p)
+        except Exception:
+            seg.close()
+            raise
+        return {"size": total, "lens": lens}, seg
 
 
 class RemoteCodec(object):
@@ -351,19 +402,20 @@ class RemoteCodec(object):
     def ping(self):
         with self._lock:
             _send_msg(self._sock, {"op": "ping"})
-            return _recv_msg(self._sock)
+            return _recv_msg(self._sock)[0]
 
     def _call(self, op, blobs):
         from .codec import FileSource
         from .exception import DataException
         from .serializer import Segments
 
-        files = {i: b.path for i, b in enumerate(blobs) if isinstance(b, FileSource)}
+        files = {str(i): b.path for i, b in enumerate(blobs) if isinstance(b, FileSource)}
         mem = [b for b in blobs if not isinstance(b, FileSource)]
         lens = [len(b) for b in mem]
         offs, total = _layout(lens)
         seg = None
         msg = {"op": op, "files": files}
+        fds = []
         try:
             if mem:
                 seg = _Segment.create(total)
@@ -378,49 +430,62 @@ class RemoteCodec(object):
                     else:
                         seg.view[o:o + ln] = b
                 del arr
-                msg.update(segment=seg.path, size=total, lens=lens)
+                msg.update(size=total, lens=lens)
             with self._lock:
-                _send_msg(self._sock, msg)
-                rep = _recv_msg(self._sock)
+                _send_msg(self._sock, msg, [seg.fd] if seg is not None else ())
+                rep, fds = _recv_msg(self._sock)
         finally:
             if seg is not None:
-                seg.unlink()
                 seg.close()
         if not rep.get("ok"):
+            for fd in fds:
+                os.close(fd)
             raise DataException("GPU batcher call failed: %s" % rep.get("error"))
-        return rep
+        return rep, fds
 
     @staticmethod
-    def _import(rep):
-        out_seg = _Segment(rep["segment"], rep["size"], False)
-        out_seg.unlink()                                   # the mapping keeps the pages until the views die
-        offs, _ = _layout(rep["lens"])
-        return [out_seg.view[o:o + ln] for o, ln in zip(offs, rep["lens"])]
+    def _import(rep, fds):
+        """The reply's segment -> one view per blob; the mapping lives as long as the views do."""
+        if not fds:
+            raise EOFError("the batcher's reply came without its segment")
+        for fd in fds[1:]:
+            os.close(fd)
+        out_seg = _Segment(fds[0], int(rep["size"]))
+        out_seg.close_fd()                                 # the mapping keeps the pages
+        lens = [int(x) for x in rep["lens"]]
+        offs, total = _layout(lens)
+        if total > out_seg.size:
+            raise ValueError("reply segment of %d bytes for %d bytes of blobs" % (out_seg.size, total))
+        return [out_seg.view[o:o + ln] for o, ln in zip(offs, lens)]
 
     def hash_batch(self, blobs):
         if not blobs:
             return []
-        return self._call("hash", list(blobs))["keys"]
+        rep, fds = self._call("hash", list(blobs))
+        for fd in fds:
+            os.close(fd)
+        return rep["keys"]
 
     def pack_batch(self, blobs):
         from .codec import Packed
 
         if not blobs:
             return [], []
-        rep = self._call("pack", list(blobs))
-        return rep["keys"], [Packed([v]) for v in self._import(rep)]
+        rep, fds = self._call("pack", list(blobs))
+        return rep["keys"], [Packed([v]) for v in self._import(rep, fds)]
 
     def unpack_batch(self, packed_blobs, as_bytes=True):
         from .codec import UnpackError
 
         if not packed_blobs:
             return []
-        rep = self._call("unpack", list(packed_blobs))
-        views = self._import(rep)
+        rep, fds = self._call("unpack", list(packed_blobs))
+        views = self._import(rep, fds)
+        errors = {int(k): v for k, v in rep["errors"].items()}
         out = []
         for i, v in enumerate(views):
-            if i in rep["errors"]:
-                out.append(UnpackError(rep["errors"][i][0]))
+            if i in errors:
+                out.append(UnpackError(errors[i][0]))
             else:
                 out.append(bytes(v) if as_bytes else v)
         return out

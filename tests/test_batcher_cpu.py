@@ -117,3 +117,49 @@ def test_forked_tasks_save_through_the_parents_batcher(server, tmp_path, monkeyp
     from metaflow_b200 import FlowDataStore, LocalStorage
     fds = FlowDataStore("ForkFlow", storage_impl=LocalStorage, ds_root=root, codec=server.codec)
     assert fds.get_task_datastore("1", "work", "3")["idx"] == 3
+
+
+def test_transport_leaves_nothing_behind(server):
+    """Segments are anonymous memory passed by descriptor: no names in /dev/shm, no descriptor growth over many calls on either
+    side (client and server share this process here), and the socket is the owner's alone."""
+    import gc
+    import stat
+
+    assert stat.S_IMODE(os.stat(server.socket_path).st_mode) == 0o600
+    c = batcher.RemoteCodec(server.socket_path)
+    rng = np.random.default_rng(9)
+    blobs = [rng.bytes(20_000), b"", b"tiny"]
+
+    def round_trip():
+        keys, packed = c.pack_batch(blobs)
+        back = c.unpack_batch([bytes(p) for p in packed] + [b"garbage"])
+        assert back[:3] == blobs and isinstance(back[3], Exception)
+        assert c.hash_batch(blobs) == keys
+
+    for _ in range(3):
+        round_trip()
+    gc.collect()
+    before = len(os.listdir("/proc/self/fd"))
+    for _ in range(40):
+        round_trip()
+    gc.collect()
+    after = len(os.listdir("/proc/self/fd"))
+    assert after <= before + 2, (before, after)
+    if os.path.isdir("/dev/shm"):
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith("mfcas_seg")]
+    c.close()
+
+
+def test_server_survives_a_malformed_client(server):
+    """Garbage on the socket (not JSON, absurd length) ends that connection, not the server."""
+    import socket as _socket
+    import struct as _struct
+
+    for payload in (_struct.pack("<Q", 5) + b"\x80\x04K\x01.", _struct.pack("<Q", 1 << 60), b"\x01\x02"):
+        s = _socket.socket(_socket.AF_UNIX, _socket.SOCK_STREAM)
+        s.connect(server.socket_path)
+        s.sendall(payload)
+        s.close()
+    c = batcher.RemoteCodec(server.socket_path)
+    assert c.ping()["ok"] and c.hash_batch([b"abc"]) == [hashlib.sha1(b"abc").hexdigest()]
+    c.close()
