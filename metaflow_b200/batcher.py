@@ -174,9 +174,10 @@ class CodecServer(object):
         self.codec = codec
         self.linger = linger
         self.max_batch_bytes = max_batch_bytes
+        self._own_dir = None
         if socket_path is None:
-            d = tempfile.mkdtemp(prefix="mfcas_srv_")
-            socket_path = os.path.join(d, "sock")
+            self._own_dir = tempfile.mkdtemp(prefix="mfcas_srv_")
+            socket_path = os.path.join(self._own_dir, "sock")
         self.socket_path = socket_path
         self._sock = None
         self._q = queue.Queue()
@@ -216,6 +217,11 @@ class CodecServer(object):
             os.unlink(self.socket_path)
         except OSError:
             pass
+        if self._own_dir is not None:
+            try:
+                os.rmdir(self._own_dir)
+            except OSError:
+                pass
 
     def __enter__(self):
         return self.start()

@@ -42,7 +42,17 @@ def _ensure_batcher():
     except Exception:  # noqa: BLE001 -- no library / no device: children run without a codec
         return None
     _server = batcher.CodecServer(codec).start()
+    import atexit
+
+    atexit.register(_stop_batcher, os.getpid())
     return _server.socket_path
+
+
+def _stop_batcher(owner_pid):
+    global _server
+    if _server is not None and os.getpid() == owner_pid:      # (a forked child inherits the object, not the server)
+        _server.stop()
+    _server = None
 
 
 def _child_setup(server_path):
@@ -85,7 +95,22 @@ def parallel_imap_unordered(func, iterable, max_parallel=None, dir=None):
         max_parallel = cpu_count()
     server_path = _ensure_batcher()
     args = iter(iterable)
-    running = [_spawn(func, a, dir, server_path) for a in islice(args, max_parallel)]
+    running = []
+    try:
+        for a in islice(args, max_parallel):
+            running.append(_spawn(func, a, dir, server_path))
+        yield from _drain(func, args, running, dir, server_path)
+    finally:
+        # an abandoned or failed iteration leaves neither orphans nor result files behind
+        for pid, path in running:
+            try:
+                os.waitpid(pid, 0)
+            except ChildProcessError:
+                pass
+            _silent_remove(path)
+
+
+def _drain(func, args, running, dir, server_path):
     delay = 0.001
     while running:
         finished = None
@@ -102,14 +127,8 @@ def parallel_imap_unordered(func, iterable, max_parallel=None, dir=None):
         k, out_path, status = finished
         running.pop(k)
         if status:
-            for pid, path in running:                        # do not leave orphans or temp files behind
-                try:
-                    os.waitpid(pid, 0)
-                except ChildProcessError:
-                    pass
-                _silent_remove(path)
             _silent_remove(out_path)
-            raise MulticoreException("Child failed")
+            raise MulticoreException("Child failed")             # (the caller's finally reaps the siblings)
         with open(out_path, "rb") as f:
             value = pickle.load(f)
         _silent_remove(out_path)

@@ -163,3 +163,14 @@ def test_server_survives_a_malformed_client(server):
     c = batcher.RemoteCodec(server.socket_path)
     assert c.ping()["ok"] and c.hash_batch([b"abc"]) == [hashlib.sha1(b"abc").hexdigest()]
     c.close()
+
+
+def test_abandoned_iteration_reaps_its_children(tmp_path):
+    """A consumer that stops early leaves no zombie children and no result files (the generator's finally waits for them)."""
+    it = parallel_imap_unordered(lambda i: i, range(8), max_parallel=4, dir=str(tmp_path))
+    first = next(it)
+    assert first in range(8)
+    it.close()
+    assert not list(tmp_path.iterdir())
+    with pytest.raises(ChildProcessError):
+        os.waitpid(-1, os.WNOHANG)                      # no child of this process is left to wait for
