@@ -311,7 +311,6 @@ struct MfSegReader {
 // (<= one symbol = 48 bits, or 3 literals + a match = 93 bits since the last point) and every 4 literals (<= 60 bits) of the
 // unrolled path.  Whole quads are read: up to 15 bytes past the end of the blob (the arenas leave 256; a caller's device
 // buffer ends on an allocation boundary at the earliest), never past the last quad that holds a byte of it.
-#define MF_RING_BYTES 2048u
 struct MfRingReader {
     const uint8_t *g;          // global address of the next quad to bring in (16-byte aligned)
     uint32_t left;             // bytes of the blob at g and beyond
@@ -323,9 +322,9 @@ struct MfRingReader {
         const uint32_t nb = left ? 16u : 0u;              // past the end: zeros, nothing is read
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(wslot), "l"(g), "r"(nb));
         if (left > 16u) { g += 16; left -= 16u; } else left = 0;
-        wslot = (wslot & ~(MF_RING_BYTES - 1u)) | ((wslot + 512u) & (MF_RING_BYTES - 1u));
+        wslot = mf_ring_next_slot(wslot);
     }
-    __device__ __forceinline__ uint32_t free_slots() const { return ((raddr - wslot) >> 9) & 3u; }   // slots behind the one being read
+    __device__ __forceinline__ uint32_t free_slots() const { return mf_ring_free_slots(raddr, wslot); }
     __device__ __forceinline__ void refill() {
         if (free_slots()) { issue(); if (free_slots()) issue(); }
         asm volatile("cp.async.commit_group;");
@@ -334,10 +333,7 @@ struct MfRingReader {
     __device__ __forceinline__ uint32_t word() {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(raddr));
-        // last word of the quad: on to the same lane's 16 bytes in the next slot (+500 inside the ring's 11 address bits; the
-        // sum is taken BEFORE it can carry out of them: lane 31's quad ends at the slot's last byte)
-        if ((raddr & 15u) == 12u) raddr = (raddr & ~(MF_RING_BYTES - 1u)) | ((raddr + 500u) & (MF_RING_BYTES - 1u));
-        else raddr += 4u;
+        raddr = mf_ring_next_word(raddr);                  // (mf_inflate_core.h: the CPU model runs the same expression)
         return v;
     }
     // ring_lane: shared address of this lane's 16 bytes in slot 0 of its warp's ring

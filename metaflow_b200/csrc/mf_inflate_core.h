@@ -211,6 +211,20 @@ MF_HD uint32_t mf_read_header_fast_t(R &br, uint32_t comp_bytes, uint8_t *lens, 
     return used;
 }
 
+// Address arithmetic of the chunk decoder's input ring (MfRingReader, mf_inflate.cuh), kept here so that the CPU model runs
+// the very expressions the kernel runs.  A warp's ring is MF_RING_BYTES = 4 slots x 32 lanes x 16 bytes, MF_RING_BYTES-aligned
+// in the shared address space; lane l's quad in slot s sits at s * 512 + l * 16.
+#define MF_RING_BYTES 2048u
+// read pointer after the word at `raddr`: +4 inside a quad; from a quad's last word to the same lane's quad in the next slot
+// (+500 inside the ring's 11 address bits, summed BEFORE it can carry out of them: lane 31's quad ends at the slot's last byte)
+MF_HD uint32_t mf_ring_next_word(uint32_t raddr) {
+    return (raddr & 15u) == 12u ? ((raddr & ~(MF_RING_BYTES - 1u)) | ((raddr + 500u) & (MF_RING_BYTES - 1u))) : raddr + 4u;
+}
+// write pointer after a quad went to `wslot`: the same lane's quad in the next slot
+MF_HD uint32_t mf_ring_next_slot(uint32_t wslot) { return (wslot & ~(MF_RING_BYTES - 1u)) | ((wslot + 512u) & (MF_RING_BYTES - 1u)); }
+// slots behind the one being read that have not been refilled yet
+MF_HD uint32_t mf_ring_free_slots(uint32_t raddr, uint32_t wslot) { return ((raddr - wslot) >> 9) & 3u; }
+
 // Whole raw-DEFLATE stream, one lane.  dst doubles as the 32 KiB window.
 // tables of one serial inflater.  The caller decides where they live: on the GPU a per-thread (local-memory) copy is
 // interleaved with the other threads' at a 128-byte stride -- a 1 KiB table is 256 cache lines and every lookup

@@ -340,4 +340,9 @@ void model_header_both(const uint8_t *src, uint64_t n, uint32_t comp_bytes, uint
     out[3] = (uint32_t)e; out[4] = e ? 0u : (uint32_t)br.bitpos(); out[5] = hl; out[6] = hd;
 }
 
+// ---- the chunk decoder's input-ring address arithmetic (the expressions MfRingReader runs on the GPU)
+uint32_t model_ring_next_word(uint32_t raddr) { return mf_ring_next_word(raddr); }
+uint32_t model_ring_next_slot(uint32_t wslot) { return mf_ring_next_slot(wslot); }
+uint32_t model_ring_free_slots(uint32_t raddr, uint32_t wslot) { return mf_ring_free_slots(raddr, wslot); }
+
 }  // extern "C"

@@ -29,6 +29,9 @@ def lib():
     L.model_gunzip_parallel.argtypes = sig + [ctypes.POINTER(ctypes.c_uint64)]
     L.model_header_both.restype = None
     L.model_header_both.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    for fn, nargs in ((L.model_ring_next_word, 1), (L.model_ring_next_slot, 1), (L.model_ring_free_slots, 2)):
+        fn.restype = ctypes.c_uint32
+        fn.argtypes = [ctypes.c_uint32] * nargs
     _lib = L
     return L
 

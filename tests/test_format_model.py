@@ -225,3 +225,70 @@ def test_fast_header_parser_equals_the_portable_one():
         m[0] = (m[0] & 0xF8) | 4
         check(bytes(m))
     assert flips > 100          # many mutated headers are still well-formed: the comparison above really ran
+
+
+def test_decoder_input_ring_arithmetic_for_every_lane():
+    """MfRingReader's address arithmetic (mf_inflate_core.h, the expressions the kernel runs): for every lane and ring
+    position the read pointer walks quad after quad through the four slots and never leaves its lane's 16 bytes; with the
+    refill policy of the kernel (fill every free slot at a refill point, at most two groups in flight, <= 16 bytes read
+    between points) every word read belongs to a quad that has landed and no slot is overwritten before it was read."""
+    import random
+    L = model_lib.lib()
+    R = 2048
+    for base in (0x9800, 0x9800 + 7 * R, 0x1009800):              # first / last warp's ring; a non-zero CTA window in the high bits
+        for lane in range(32):
+            ring_lane = base + lane * 16
+            # plain walk
+            a, seq = ring_lane, []
+            for _ in range(64):
+                seq.append(a)
+                a = L.model_ring_next_word(a)
+            assert seq == [base + ((i // 4) % 4) * 512 + lane * 16 + (i % 4) * 4 for i in range(64)], lane
+            w = ring_lane
+            for k in range(9):
+                assert w == base + (k % 4) * 512 + lane * 16
+                w = L.model_ring_next_slot(w)
+    # the kernel's policy, driven through the same expressions
+    for lane in (0, 5, 31):
+        for skip_words in range(4):
+            for seed in range(6):
+                rnd = random.Random(seed * 131 + lane)
+                ring_lane = 0xD000 + lane * 16
+                wslot, raddr = ring_lane, ring_lane + 4 * skip_words
+                slots, groups, cur, landed, state = {}, [], [], set(), {"qn": 0, "reading": 0}
+
+                def issue():
+                    nonlocal wslot
+                    old = slots.get(wslot)
+                    assert old is None or old < state["reading"], "slot overwritten before it was read"
+                    slots[wslot] = state["qn"]; cur.append(state["qn"]); state["qn"] += 1
+                    wslot = L.model_ring_next_slot(wslot)
+
+                def commit_and_wait(n):
+                    groups.append(list(cur)); cur.clear()
+                    for g in groups[:len(groups) - n] if n else groups:
+                        landed.update(g)
+
+                def word():
+                    nonlocal raddr
+                    q = slots[raddr & ~15]
+                    assert q in landed and q == state["reading"]
+                    nxt = L.model_ring_next_word(raddr)
+                    if (raddr & 15) == 12:
+                        state["reading"] += 1
+                    raddr = nxt
+                    return q
+
+                for _ in range(4):
+                    issue()
+                commit_and_wait(0)
+                for _ in range(3):
+                    word()
+                for _ in range(300):
+                    if L.model_ring_free_slots(raddr, wslot):
+                        issue()
+                        if L.model_ring_free_slots(raddr, wslot):
+                            issue()
+                    commit_and_wait(2)
+                    for _ in range(rnd.randint(0, 4)):
+                        word()
